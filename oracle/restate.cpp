@@ -216,7 +216,6 @@ bool Scatter(const Scene& sc, int matId, const Ray& r_in, const Hit& rec, f3& at
             ++rayCount;
             Ray sr; sr.orig = rec.pos; sr.dir = l;
             int hitID = HitSpheres(sr, sc, kMinT, kMaxT, lightHit);
-            if (hitID >= sc.count) ++padHits;
             if (hitID == i)
             {
                 float omega = 2 * kPI * (1 - cosAMax);
@@ -292,12 +291,21 @@ f3 Trace(const Scene& sc, Ray r, long long& rayCount, uint32_t& state, long long
         Hit rec;
         ++rayCount;
         int id = HitSpheres(r, sc, kMinT, kMaxT, rec);
-        if (id >= sc.count) { ++padHits; id = -1 - id; }
+        if (id >= sc.count) ++padHits;
         if (id >= 0)
         {
             Ray scattered;
             f3 attenuation, lightE;
-            const MaterialRaw& mat = sc.mats[id];
+            // id >= count: the ray "hit" a padded impossible sphere (Maths.h:381-387; possible through
+            // rounding when the ray points almost exactly at (10000,10000,10000)). The reference then reads
+            // s_SphereMats[count] out of bounds (Test.cpp:205) — undefined behaviour. In the reference build
+            // made by oracle/Makefile those bytes are .bss alignment padding (type = 0 = Lambert,
+            // albedo.x = 0) followed by heap-pointer bits of s_SpheresSoA (ASLR-dependent albedo.yz /
+            // emissive). We restate the CONTROL FLOW the reference binary takes (a Lambert scatter, so the RNG
+            // stream and ray counts stay identical) with albedo = emissive = 0; the colour of such a pixel is
+            // not reproducible by the reference itself. mats[count] holds that all-zero material.
+            const MaterialRaw& mat = sc.mats[id >= sc.count ? sc.count : id];
+            if (id >= sc.count) id = sc.count;
             f3 matE = ld3(mat.emissive);
             if (depth < kMaxDepth && Scatter(sc, id, r, rec, attenuation, scattered, lightE, rayCount, state, padHits))
             {
@@ -312,19 +320,11 @@ f3 Trace(const Scene& sc, Ray r, long long& rayCount, uint32_t& state, long long
             result = matE; // Test.cpp:218-221
             break;
         }
-        else if (id == -1)
+        else
         {
             // sky, Test.cpp:229-231
             float t = 0.5f * (r.dir.y + 1.0f);
             result = ((1.0f - t) * mk(1.0f, 1.0f, 1.0f) + t * mk(0.5f, 0.7f, 1.0f)) * 0.3f;
-            break;
-        }
-        else
-        {
-            // The ray "hit" one of the padded impossible spheres (Maths.h:381-387). The reference then
-            // indexes s_SphereMats out of bounds (undefined behaviour); we report it via padHits and end
-            // the path with black so the caller can see that parity is undefined for this image.
-            result = mk(0, 0, 0);
             break;
         }
     }
@@ -345,8 +345,10 @@ Ray GetRay(const CameraRaw& c, float s, float t, uint32_t& state)
 }
 
 // Test.cpp:266-300, one row
+struct PadLog { std::atomic<int> n; int cap; int* xyf; };
+
 void TraceRow(const Scene& sc, int y, int frameCount, int w, int h, unsigned flags, int spp, float* backbuffer,
-              long long& rayCountOut, long long& padHits)
+              long long& rayCountOut, long long& padHits, PadLog* padLog)
 {
     float invWidth = 1.0f / w;
     float invHeight = 1.0f / h;
@@ -359,12 +361,18 @@ void TraceRow(const Scene& sc, int y, int frameCount, int w, int h, unsigned fla
     for (int x = 0; x < w; ++x)
     {
         f3 col = mk(0, 0, 0);
+        long long padBefore = padHits;
         for (int s = 0; s < spp; s++)
         {
             float u = float(x + RandomFloat01(state)) * invWidth;
             float v = float((uint32_t)y + RandomFloat01(state)) * invHeight;
             Ray r = GetRay(sc.cam, u, v, state);
             col = col + Trace(sc, r, rayCount, state, padHits);
+        }
+        if (padHits != padBefore && padLog)
+        {
+            int k = padLog->n.fetch_add(1);
+            if (k < padLog->cap) { padLog->xyf[3 * k] = x; padLog->xyf[3 * k + 1] = y; padLog->xyf[3 * k + 2] = frameCount; }
         }
         col = col * (1.0f / float(spp));
         f3 prev = mk(bb[0], bb[1], bb[2]);
@@ -382,18 +390,22 @@ extern "C" {
 // spheres: count x {cx,cy,cz,radius,invRadius} (invRadius recomputed like UpdateTest, Test.cpp:325);
 // mats: count x 36 B; cam: 88 B. Renders frames [frame0, frame0+nframes) like the reference shells do
 // (UpdateTest + DrawTest per frame) into buf (w*h*4, caller-owned, read as `prev`).
-// rays[i] = rays of frame i; pad_hits (optional) = number of rays that hit a padded sphere (reference UB).
+// rays[i] = rays of frame i; pad_hits (optional) = number of path rays that hit a padded sphere (reference
+// UB, see Trace()); pad_xyf (optional, pad_cap triples) = (x, y, frame) of the pixels those rays belong to.
 int orc_render(const float* spheres, const void* mats, int count, const void* cam,
                int w, int h, int frame0, int nframes, unsigned flags, int spp, int simd_tie,
-               float* buf, long long* rays, long long* pad_hits, double* seconds, int nthreads)
+               float* buf, long long* rays, long long* pad_hits, double* seconds, int nthreads,
+               int* pad_xyf, int pad_cap)
 {
+    PadLog padLog; padLog.n = 0; padLog.cap = pad_xyf ? pad_cap : 0; padLog.xyf = pad_xyf;
     Scene sc;
     sc.count = count;
     sc.simdCount = (count + 3) / 4 * 4;
     sc.simdTie = simd_tie;
     sc.cx.assign(sc.simdCount, 10000.0f); sc.cy = sc.cx; sc.cz = sc.cx;
     sc.sqR.assign(sc.simdCount, 0.0f); sc.invR.assign(sc.simdCount, 0.0f);
-    sc.spheres.resize(count); sc.mats.resize(count);
+    sc.spheres.resize(count); sc.mats.resize(count + 1);
+    memset(&sc.mats[count], 0, sizeof(MaterialRaw)); // the out-of-bounds "pad" material, see Trace()
     memcpy(sc.spheres.data(), spheres, (size_t)count * sizeof(SphereRaw));
     memcpy(sc.mats.data(), mats, (size_t)count * sizeof(MaterialRaw));
     memcpy(&sc.cam, cam, sizeof(CameraRaw));
@@ -422,7 +434,7 @@ int orc_render(const float* spheres, const void* mats, int count, const void* ca
                 int y0 = nextRow.fetch_add(4); // Test.cpp:359 min range 4 rows
                 if (y0 >= h) break;
                 for (int y = y0; y < y0 + 4 && y < h; ++y)
-                    TraceRow(sc, y, frame0 + f, w, h, flags, spp, buf, myRays, myPad);
+                    TraceRow(sc, y, frame0 + f, w, h, flags, spp, buf, myRays, myPad, &padLog);
             }
             rc += myRays; ph += myPad;
         };

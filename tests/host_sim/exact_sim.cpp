@@ -1,0 +1,57 @@
+// Test-only: HOST build of the product's integrator source (toypathtracer_b200/csrc/tpt_integrator.cuh, EXACT
+// instantiation, SerialHitter) so its logic can be checked bit-for-bit against the oracle on a machine without
+// a GPU. Never linked into the product library; the product has no CPU path.
+// Build: g++ -O2 -std=c++17 -ffp-contract=off -mfma (fma only reaches the explicit __builtin_fma calls).
+#include "../../toypathtracer_b200/csrc/tpt_integrator.cuh"
+#include "../../toypathtracer_b200/csrc/tpt_scene_pack.h"
+#include <thread>
+#include <atomic>
+#include <vector>
+
+using namespace tpt;
+
+extern "C" int sim_render_exact(const void* spheres, const void* mats, int count, const void* cam,
+                                int w, int h, int frame0, int nframes, unsigned flags, int spp,
+                                float* buf, long long* rays, int nthreads)
+{
+    std::vector<unsigned char> blob; SceneBlobLayout L; int nLights;
+    pack_scene_blob((const Sphere20*)spheres, (const Material36*)mats, count, nullptr, 0, blob, L, nLights);
+    SceneView sc = scene_view_from_blob(blob.data(), L, count, nLights);
+    Camera88 c; memcpy(&c, cam, sizeof(c));
+    float invW = 1.0f / w, invH = 1.0f / h;
+    if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
+    SerialHitter<true> hitter;
+    for (int f = 0; f < nframes; ++f)
+    {
+        int frame = frame0 + f;
+        float lerpFac = lerp_fac(frame, flags);
+        std::atomic<int> next(0);
+        std::atomic<long long> total(0);
+        auto work = [&]() {
+            long long mine = 0;
+            for (;;)
+            {
+                int y = next.fetch_add(1);
+                if (y >= h) break;
+                uint32_t state = row_seed(y, frame);
+                unsigned rc = 0;
+                float* bb = buf + (size_t)y * w * 4;
+                for (int x = 0; x < w; ++x, bb += 4)
+                {
+                    V3 col = pixel_exact(sc, c, x, y, spp, invW, invH, state, rc, hitter);
+                    V3 prev = v3(bb[0], bb[1], bb[2]);
+                    col = prev * lerpFac + col * (1.0f - lerpFac);
+                    bb[0] = col.x; bb[1] = col.y; bb[2] = col.z;
+                }
+                mine += rc;
+            }
+            total += mine;
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthreads; ++t) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+        if (rays) rays[f] = total.load();
+    }
+    return 0;
+}

@@ -1,0 +1,488 @@
+// The per-pixel hot loop of the reference (Camera::GetRay -> Trace -> HitWorld/HitSpheres -> Scatter),
+// written once for both arithmetic modes:
+//
+//   EXACT = true   "replay": every float operation in the order the reference's C++ performs it, no FMA
+//                  contraction (the translation unit is compiled with -fmad=false; host_sim with
+//                  -ffp-contract=off), IEEE division/sqrt, glibc-faithful sinf/cosf/powf (tpt_libm.cuh), the
+//                  reference's RNG stream (one XorShift32 chain per (frame,row), Test.cpp:280) and its
+//                  back-to-front colour fold (Test.cpp:216). Output is bit-identical to the reference build.
+//   EXACT = false  "fast": same estimator, same samplers, per-path RNG streams, FMA contraction and fast
+//                  transcendental intrinsics allowed, colour folded front-to-back.
+//
+// Reference citations are to /root/reference/Cpp/Source/.
+#pragma once
+#include "tpt_libm.cuh"
+#include "tpt_types.h"
+
+#if defined(__CUDACC__)
+#define TPT_D __device__ __forceinline__
+#else
+#define TPT_D inline
+#endif
+
+namespace tpt {
+
+// Maths.h:9, Test.cpp:71-73
+#define TPT_PI 3.1415926f
+#define TPT_MIN_T 0.001f
+#define TPT_MAX_T 1.0e7f
+#define TPT_MAX_DEPTH 10
+
+// ---- float3 (Maths.h:23-115 SSE semantics, scalar form proven bit-identical in SURVEY §9.2) ----------------
+struct V3 { float x, y, z; };
+TPT_HD V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+TPT_HD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+TPT_HD V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+TPT_HD V3 operator*(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+TPT_HD V3 operator*(V3 a, float b) { return v3(a.x * b, a.y * b, a.z * b); }
+TPT_HD V3 operator*(float a, V3 b) { return v3(a * b.x, a * b.y, a * b.z); }
+// Maths.h:85: -a is (0 - a) in the SSE float3 (keeps +0 for +0)
+TPT_HD V3 neg(V3 a) { return v3(0.0f - a.x, 0.0f - a.y, 0.0f - a.z); }
+// Maths.h:114-115: (x + y) + z
+TPT_HD float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// Maths.h:98-105
+TPT_HD V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+TPT_HD V3 ld3(const float* p) { return v3(p[0], p[1], p[2]); }
+
+template <bool EXACT> struct M
+{
+    // IEEE-exact in EXACT mode; approximate reciprocal / rsqrt forms allowed otherwise.
+    static TPT_HD float sqrt_(float x)
+    {
+#if defined(__CUDA_ARCH__)
+        return EXACT ? __fsqrt_rn(x) : sqrtf(x);
+#else
+        return sqrtf(x);
+#endif
+    }
+    static TPT_HD float div_(float a, float b)
+    {
+#if defined(__CUDA_ARCH__)
+        return EXACT ? __fdiv_rn(a, b) : __fdividef(a, b);
+#else
+        return a / b;
+#endif
+    }
+    static TPT_HD float sin_(float a)
+    {
+        if (EXACT) { float r; if (tptlibm::sinf_glibc(a, &r)) return r; return sinf(a); }
+#if defined(__CUDA_ARCH__)
+        return __sinf(a);
+#else
+        return sinf(a);
+#endif
+    }
+    static TPT_HD float cos_(float a)
+    {
+        if (EXACT) { float r; if (tptlibm::cosf_glibc(a, &r)) return r; return cosf(a); }
+#if defined(__CUDA_ARCH__)
+        return __cosf(a);
+#else
+        return cosf(a);
+#endif
+    }
+    // powf(x, 5) (Maths.h:331)
+    static TPT_HD float pow5_(float x)
+    {
+        if (EXACT) return tptlibm::powf_glibc(x, 5.0f);
+        float x2 = x * x;
+        return x2 * x2 * x;
+    }
+    // Maths.h:299-301: normalize(v) = v * (1.0f / sqrtf(dot(v,v)))
+    static TPT_HD V3 normalize(V3 v)
+    {
+#if defined(__CUDA_ARCH__)
+        if (!EXACT) return v * rsqrtf(dot(v, v));
+#endif
+        return v * div_(1.0f, sqrt_(dot(v, v)));
+    }
+};
+
+// ---- RNG + samplers (Maths.cpp:5-47) ---------------------------------------------------------------------
+TPT_HD uint32_t XorShift32(uint32_t& state)
+{
+    uint32_t x = state;
+    x ^= x << 13;
+    x ^= x >> 17;
+    x ^= x << 15;
+    state = x;
+    return x;
+}
+// (x & 0xFFFFFF) / 16777216.0f is exact (24-bit integer times 2^-24)
+TPT_HD float RandomFloat01(uint32_t& state) { return (float)(XorShift32(state) & 0xFFFFFF) * (1.0f / 16777216.0f); }
+
+// Maths.cpp:20-28; g++ evaluates float3(R(), R(), 0) right to left: y = 1st draw, x = 2nd
+TPT_HD V3 RandomInUnitDisk(uint32_t& state)
+{
+    V3 p;
+    do
+    {
+        float y = RandomFloat01(state);
+        float x = RandomFloat01(state);
+        p = 2.0f * v3(x, y, 0.0f) - v3(1.0f, 1.0f, 0.0f);
+    } while (dot(p, p) >= 1.0f);
+    return p;
+}
+// Maths.cpp:30-37; z = 1st draw, y = 2nd, x = 3rd
+TPT_HD V3 RandomInUnitSphere(uint32_t& state)
+{
+    V3 p;
+    do
+    {
+        float z = RandomFloat01(state);
+        float y = RandomFloat01(state);
+        float x = RandomFloat01(state);
+        p = 2.0f * v3(x, y, z) - v3(1.0f, 1.0f, 1.0f);
+    } while (dot(p, p) >= 1.0f);
+    return p;
+}
+// Maths.cpp:39-47
+template <bool EXACT> TPT_HD V3 RandomUnitVector(uint32_t& state)
+{
+    float z = RandomFloat01(state) * 2.0f - 1.0f;
+    float a = RandomFloat01(state) * 2.0f * TPT_PI;
+    float r = M<EXACT>::sqrt_(1.0f - z * z);
+    float x = r * M<EXACT>::cos_(a);
+    float y = r * M<EXACT>::sin_(a);
+    return v3(x, y, z);
+}
+
+struct Ray { V3 orig, dir; };
+
+// Maths.h:437-442
+template <bool EXACT> TPT_HD Ray GetRay(const Camera88& c, float s, float t, uint32_t& state)
+{
+    V3 rd = c.lensRadius * RandomInUnitDisk(state);
+    V3 offset = ld3(c.uu) * rd.x + ld3(c.vv) * rd.y;
+    Ray r;
+    r.orig = ld3(c.origin) + offset;
+    r.dir = M<EXACT>::normalize(ld3(c.lowerLeftCorner) + s * ld3(c.horizontal) + t * ld3(c.vertical) - ld3(c.origin) - offset);
+    return r;
+}
+
+// ---- HitSpheres (Maths.cpp:50-203) ------------------------------------------------------------------------
+// One sphere test, Maths.cpp:97-117 / 171-190. Candidate order is the SSE build's: smaller t wins; on an
+// exact tie the lower SIMD lane (id & 3) wins, then the lower id (Maths.cpp:113-117 keeps the first hit per
+// lane with a strict '<', Maths.cpp:126-152 picks the lowest lane among equal minima).
+TPT_HD bool hit_better(float t, int id, float bestT, int bestId)
+{
+    if (t < bestT) return true;
+    if (t == bestT && bestId >= 0)
+    {
+        int l = id & 3, bl = bestId & 3;
+        return l < bl || (l == bl && id < bestId);
+    }
+    return false;
+}
+
+template <bool EXACT> TPT_HD void test_sphere(const Q4 s, int i, V3 o, V3 d, float tMin, float& bestT, int& bestId)
+{
+    float coX = s.x - o.x;
+    float coY = s.y - o.y;
+    float coZ = s.z - o.z;
+    float nb = coX * d.x + coY * d.y + coZ * d.z;
+    float c = coX * coX + coY * coY + coZ * coZ - s.w;
+    float discr = nb * nb - c;
+    if (discr > 0.0f)
+    {
+        float discrSq = M<EXACT>::sqrt_(discr);
+        float t = nb - discrSq;
+        if (t <= tMin) t = nb + discrSq;
+        if (t > tMin && hit_better(t, i, bestT, bestId)) { bestT = t; bestId = i; }
+    }
+}
+
+// Every lane sweeps all spheres itself (lane = ray).
+template <bool EXACT> struct SerialHitter
+{
+    TPT_HD int hit(const SceneView& sc, V3 o, V3 d, float tMin, float tMax, float& tOut) const
+    {
+        float bestT = tMax;
+        int bestId = -1;
+        for (int i = 0; i < sc.simdCount; ++i) test_sphere<EXACT>(sc.sph[i], i, o, d, tMin, bestT, bestId);
+        tOut = bestT;
+        return bestId;
+    }
+};
+
+#if defined(__CUDACC__)
+// LANES lanes of a warp share one ray: lane `sub` sweeps spheres sub, sub+LANES, ... (a warp-wide SoA sweep
+// from shared memory) and the nearest hit is reduced with shuffles under the same total order.
+template <bool EXACT, int LANES> struct GroupHitter
+{
+    unsigned mask;
+    int sub;
+    __device__ __forceinline__ int hit(const SceneView& sc, V3 o, V3 d, float tMin, float tMax, float& tOut) const
+    {
+        float bestT = tMax;
+        int bestId = -1;
+        for (int i = sub; i < sc.simdCount; i += LANES) test_sphere<EXACT>(sc.sph[i], i, o, d, tMin, bestT, bestId);
+#pragma unroll
+        for (int off = LANES / 2; off > 0; off >>= 1)
+        {
+            float ot = __shfl_xor_sync(mask, bestT, off);
+            int oid = __shfl_xor_sync(mask, bestId, off);
+            if (oid >= 0 && hit_better(ot, oid, bestT, bestId)) { bestT = ot; bestId = oid; }
+        }
+        tOut = bestT;
+        return bestId;
+    }
+};
+template <bool EXACT> struct GroupHitter<EXACT, 1> : SerialHitter<EXACT> { unsigned mask; int sub; };
+#endif
+
+// ---- materials ---------------------------------------------------------------------------------------------
+struct Mat { V3 albedo, emissive; float roughness, ri; int type; };
+TPT_HD int f_as_i(float f) { return (int)tptlibm::f2u(f); }
+TPT_HD Mat load_mat(const SceneView& sc, int id)
+{
+    Q4 a = sc.matA[id], b = sc.matB[id];
+    Mat m;
+    m.albedo = v3(a.x, a.y, a.z);
+    m.type = f_as_i(a.w);
+    m.emissive = v3(b.x, b.y, b.z);
+    m.roughness = b.w;
+    m.ri = sc.matRi[id];
+    return m;
+}
+
+// Maths.h:310-313
+TPT_HD V3 reflect(V3 v, V3 n) { return v - (2.0f * dot(v, n)) * n; }
+// Maths.h:315-326
+template <bool EXACT> TPT_HD bool refract(V3 v, V3 n, float nint, V3& outRefracted)
+{
+    float dt = dot(v, n);
+    float discr = 1.0f - nint * nint * (1.0f - dt * dt);
+    if (discr > 0.0f)
+    {
+        outRefracted = nint * (v - n * dt) - n * M<EXACT>::sqrt_(discr);
+        return true;
+    }
+    return false;
+}
+// Maths.h:327-332
+template <bool EXACT> TPT_HD float schlick(float cosine, float ri)
+{
+    float r0 = M<EXACT>::div_(1.0f - ri, 1.0f + ri);
+    r0 = r0 * r0;
+    return r0 + (1.0f - r0) * M<EXACT>::pow5_(1.0f - cosine);
+}
+
+// Explicit light sampling for one emissive sphere, Test.cpp:102-132. Returns the shadow-ray direction and the
+// radiance it carries if the ray reaches the light (the caller shoots the ray).
+template <bool EXACT>
+TPT_HD void sample_light(const LightRec& L, V3 pos, V3 normal, V3 rdir, V3 albedo, uint32_t& state, V3& l, V3& contrib)
+{
+    V3 sc = v3(L.cx, L.cy, L.cz);
+    V3 sw = M<EXACT>::normalize(sc - pos);
+    V3 su = M<EXACT>::normalize(cross(fabsf(sw.x) > 0.01f ? v3(0, 1, 0) : v3(1, 0, 0), sw));
+    V3 sv = cross(sw, su);
+    V3 pc = pos - sc;
+    float cosAMax = M<EXACT>::sqrt_(1.0f - M<EXACT>::div_(L.radius * L.radius, dot(pc, pc)));
+    float eps1 = RandomFloat01(state), eps2 = RandomFloat01(state);
+    float cosA = 1.0f - eps1 + eps1 * cosAMax;
+    float sinA = M<EXACT>::sqrt_(1.0f - cosA * cosA);
+    float phi = 2.0f * TPT_PI * eps2;
+    l = su * (M<EXACT>::cos_(phi) * sinA) + sv * (M<EXACT>::sin_(phi) * sinA) + sw * cosA;
+    float omega = 2.0f * TPT_PI * (1.0f - cosAMax);
+    V3 nl = dot(normal, rdir) < 0.0f ? normal : neg(normal);
+    float d = dot(l, nl);
+    float m = (0.0f < d) ? d : 0.0f;                      // std::max(0.0f, d), Test.cpp:131
+    contrib = (albedo * v3(L.ex, L.ey, L.ez)) * M<EXACT>::div_(m * omega, TPT_PI);
+}
+
+// Test.cpp:83-193 for Metal and Dielectric (Lambert is handled by the callers because of its shadow rays).
+// Returns false when the path ends (Metal scattering below the surface, unknown type).
+template <bool EXACT>
+TPT_HD bool scatter_specular(const Mat& mat, V3 rdir, V3 pos, V3 normal, uint32_t& state, V3& attenuation, V3& outDir)
+{
+    if (mat.type == kMetal) // Test.cpp:137-150
+    {
+        V3 refl = reflect(rdir, normal);
+        V3 rnd = RandomInUnitSphere(state);              // drawn even when roughness == 0
+        outDir = M<EXACT>::normalize(refl + mat.roughness * rnd);
+        attenuation = mat.albedo;
+        return dot(outDir, normal) > 0.0f;
+    }
+    if (mat.type == kDielectric) // Test.cpp:151-186
+    {
+        V3 outwardN;
+        V3 refl = reflect(rdir, normal);
+        float nint;
+        attenuation = v3(1, 1, 1);
+        V3 refr = v3(0, 0, 0);
+        float reflProb;
+        float cosine;
+        float dn = dot(rdir, normal);
+        if (dn > 0.0f)
+        {
+            outwardN = neg(normal);
+            nint = mat.ri;
+            cosine = mat.ri * dn;
+        }
+        else
+        {
+            outwardN = normal;
+            nint = M<EXACT>::div_(1.0f, mat.ri);
+            cosine = -dn;
+        }
+        if (refract<EXACT>(rdir, outwardN, nint, refr)) reflProb = schlick<EXACT>(cosine, mat.ri);
+        else reflProb = 1.0f;
+        if (RandomFloat01(state) < reflProb) outDir = M<EXACT>::normalize(refl);
+        else outDir = M<EXACT>::normalize(refr);
+        return true;
+    }
+    attenuation = v3(1, 0, 1); // Test.cpp:187-191
+    return false;
+}
+
+// Sky, Test.cpp:229-231
+TPT_HD V3 sky(V3 dir)
+{
+    float t = 0.5f * (dir.y + 1.0f);
+    return ((1.0f - t) * v3(1.0f, 1.0f, 1.0f) + t * v3(0.5f, 0.7f, 1.0f)) * 0.3f;
+}
+
+// Test.cpp:195-234 (+ Scatter's Lambert branch, Test.cpp:86-136) for ONE camera ray, reference order.
+// The recursion `matE + lightE + attenuation * Trace(...)` (Test.cpp:216) is unrolled with an explicit stack and
+// folded back to front so the rounding sequence is the reference's.
+template <class Hitter>
+TPT_HD V3 trace_exact(const SceneView& sc, Ray r, uint32_t& state, unsigned& rayCount, const Hitter& hitter)
+{
+    V3 e[TPT_MAX_DEPTH + 1], a[TPT_MAX_DEPTH + 1];
+    int n = 0;
+    bool doMaterialE = true;
+    V3 result;
+    for (int depth = 0;; ++depth)
+    {
+        ++rayCount;
+        float t;
+        int id = hitter.hit(sc, r.orig, r.dir, TPT_MIN_T, TPT_MAX_T, t);
+        if (id < 0) { result = sky(r.dir); break; }
+        // Maths.cpp:156-157 / 195-196
+        Q4 s = sc.sph[id];
+        V3 pos = r.orig + r.dir * t;
+        V3 normal = (pos - v3(s.x, s.y, s.z)) * sc.invRadius[id];
+        // id >= count: a padded "impossible" sphere was hit; the reference reads s_SphereMats out of bounds
+        // there (an all-zero Lambert in its build); entry [count] of the material arrays restates that.
+        int mid = id < sc.count ? id : sc.count;
+        Mat mat = load_mat(sc, mid);
+        V3 matE = mat.emissive;
+        if (depth >= TPT_MAX_DEPTH) { result = matE; break; }
+        V3 attenuation, lightE = v3(0, 0, 0), outDir;
+        if (mat.type == kLambert)
+        {
+            // Test.cpp:89-92
+            V3 target = pos + normal + RandomUnitVector<true>(state);
+            outDir = M<true>::normalize(target - pos);
+            attenuation = mat.albedo;
+            for (int j = 0; j < sc.nLights; ++j) // Test.cpp:96-133
+            {
+                const LightRec L = sc.lights[j];
+                if (L.id == mid) continue; // Test.cpp:100
+                V3 l, contrib;
+                sample_light<true>(L, pos, normal, r.dir, mat.albedo, state, l, contrib);
+                ++rayCount;
+                float ts;
+                int hid = hitter.hit(sc, pos, l, TPT_MIN_T, TPT_MAX_T, ts);
+                if (hid == L.id) lightE = lightE + contrib;
+            }
+        }
+        else if (!scatter_specular<true>(mat, r.dir, pos, normal, state, attenuation, outDir))
+        {
+            result = matE; // Test.cpp:218-221
+            break;
+        }
+        if (!doMaterialE) matE = v3(0, 0, 0);   // Test.cpp:210
+        doMaterialE = (mat.type != kLambert);  // Test.cpp:214
+        e[n] = matE + lightE;
+        a[n] = attenuation;
+        ++n;
+        r.orig = pos;
+        r.dir = outDir;
+    }
+    for (int k = n - 1; k >= 0; --k) result = e[k] + a[k] * result;
+    return result;
+}
+
+// Same estimator, front-to-back accumulation, no stack (fast mode).
+template <class Hitter>
+TPT_HD V3 trace_fast(const SceneView& sc, Ray r, uint32_t& state, unsigned& rayCount, const Hitter& hitter)
+{
+    V3 col = v3(0, 0, 0), thr = v3(1, 1, 1);
+    bool doMaterialE = true;
+    for (int depth = 0;; ++depth)
+    {
+        ++rayCount;
+        float t;
+        int id = hitter.hit(sc, r.orig, r.dir, TPT_MIN_T, TPT_MAX_T, t);
+        if (id < 0) { col = col + thr * sky(r.dir); break; }
+        Q4 s = sc.sph[id];
+        V3 pos = r.orig + r.dir * t;
+        V3 normal = (pos - v3(s.x, s.y, s.z)) * sc.invRadius[id];
+        int mid = id < sc.count ? id : sc.count;
+        Mat mat = load_mat(sc, mid);
+        if (depth >= TPT_MAX_DEPTH) { col = col + thr * mat.emissive; break; }
+        V3 attenuation, outDir;
+        if (mat.type == kLambert)
+        {
+            V3 target = pos + normal + RandomUnitVector<false>(state);
+            outDir = M<false>::normalize(target - pos);
+            attenuation = mat.albedo;
+            if (doMaterialE) col = col + thr * mat.emissive;
+            for (int j = 0; j < sc.nLights; ++j)
+            {
+                const LightRec L = sc.lights[j];
+                if (L.id == mid) continue;
+                V3 l, contrib;
+                sample_light<false>(L, pos, normal, r.dir, mat.albedo, state, l, contrib);
+                ++rayCount;
+                float ts;
+                int hid = hitter.hit(sc, pos, l, TPT_MIN_T, TPT_MAX_T, ts);
+                if (hid == L.id) col = col + thr * contrib;
+            }
+            doMaterialE = false;
+        }
+        else
+        {
+            bool ok = scatter_specular<false>(mat, r.dir, pos, normal, state, attenuation, outDir);
+            if (!ok) { col = col + thr * mat.emissive; break; }   // Test.cpp:218-221: full matE
+            if (doMaterialE) col = col + thr * mat.emissive;
+            doMaterialE = true;
+        }
+        thr = thr * attenuation;
+        r.orig = pos;
+        r.dir = outDir;
+    }
+    return col;
+}
+
+// Test.cpp:272-276
+TPT_HD float lerp_fac(int frameCount, unsigned flags)
+{
+    float lerpFac = M<true>::div_((float)frameCount, (float)(frameCount + 1));
+    if (flags & 1u) lerpFac *= 0.9f;      // kFlagAnimate, DO_ANIMATE_SMOOTHING (Config.h:23)
+    if (!(flags & 2u)) lerpFac = 0.0f;    // !kFlagProgressive
+    return lerpFac;
+}
+
+// Test.cpp:280
+TPT_HD uint32_t row_seed(int y, int frameCount) { return ((uint32_t)y * 9781u + (uint32_t)frameCount * 6271u) | 1u; }
+
+// One pixel of the exact stream: Test.cpp:283-291 (col already multiplied by 1/spp).
+template <class Hitter>
+TPT_HD V3 pixel_exact(const SceneView& sc, const Camera88& cam, int x, int y, int spp, float invWidth, float invHeight,
+                      uint32_t& state, unsigned& rayCount, const Hitter& hitter)
+{
+    V3 col = v3(0, 0, 0);
+    for (int s = 0; s < spp; s++)
+    {
+        float u = ((float)x + RandomFloat01(state)) * invWidth;
+        float v = ((float)(uint32_t)y + RandomFloat01(state)) * invHeight;
+        Ray r = GetRay<true>(cam, u, v, state);
+        col = col + trace_exact(sc, r, state, rayCount, hitter);
+    }
+    return col * M<true>::div_(1.0f, (float)spp);
+}
+
+} // namespace tpt
