@@ -1,0 +1,95 @@
+/* tpt_b200 — C-ABI of the B200-native ToyPathTracer hot path.
+ *
+ * This library replaces what the reference's DrawTest() does on the CPU (Cpp/Source/Test.cpp:344-367 ->
+ * TraceRowJob :266-300 -> Trace :195-234 -> HitWorld/HitSpheres Maths.cpp:50-203 -> Scatter :83-193) with
+ * hand-written sm_100a CUDA kernels. It sits exactly where the reference's own GPU back-ends sit: the shell
+ * calls UpdateTest(), pulls the scene with GetObjectCount()/GetSceneDesc() (raw 20 B Sphere / 36 B Material /
+ * 88 B Camera structs + emissive id list, Cpp/Windows/TestWin.cpp:258-283) and dispatches a kernel instead of
+ * DrawTest(). Plain pointers and sizes only; every function returns 0 on success or a CUDA error code
+ * (tpt_last_error() gives the text). There is no CPU fallback: without a CUDA device tpt_create() fails.
+ *
+ * A drop-in C++ translation unit exporting the six functions of Cpp/Source/Test.h on top of this ABI is
+ * toypathtracer_b200/csrc/test_shim.cpp.
+ */
+#ifndef TPT_B200_H
+#define TPT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tpt_context tpt_context;
+
+/* Rendering modes.
+ * TPT_MODE_EXACT  bit-identical to the reference C++ path: per-(frame,row) XorShift32 streams (Test.cpp:280),
+ *                 no FMA contraction, glibc-faithful sinf/cosf/powf, back-to-front colour fold. Same pixels,
+ *                 same ray counts.
+ * TPT_MODE_FAST   same estimator, one RNG stream per (pixel, sample, frame); statistically equivalent image and
+ *                 rays/sample. Throughput mode. */
+#define TPT_MODE_EXACT 0
+#define TPT_MODE_FAST 1
+
+/* testFlags of Cpp/Source/Test.h:4-8 */
+#define TPT_FLAG_ANIMATE 1u
+#define TPT_FLAG_PROGRESSIVE 2u
+
+/* Replaces InitializeTest() (Test.cpp:240-246, which only creates the CPU task scheduler): binds a context to
+ * CUDA device `device`. */
+int tpt_create(int device, tpt_context** out);
+/* Replaces ShutdownTest() (Test.cpp:248-253). */
+void tpt_destroy(tpt_context* ctx);
+int tpt_device_count(void);
+const char* tpt_last_error(tpt_context* ctx);
+
+/* Takes exactly what GetSceneDesc() exports (Test.cpp:377-384): `count` 20 B spheres, `count` 36 B materials,
+ * one 88 B camera, the emissive sphere ids (Test.cpp:321-338). emissives == NULL derives the list from the
+ * materials the way UpdateTest does. invRadius is recomputed (Maths.h:359). Call after every UpdateTest(). */
+int tpt_set_scene(tpt_context* ctx, const void* spheres20, const void* materials36, int count,
+                  const void* camera88, const int* emissives, int emissiveCount);
+/* Camera only (UpdateTest rebuilds it every frame from the aspect ratio, Test.cpp:341). */
+int tpt_set_camera(tpt_context* ctx, const void* camera88);
+
+/* DO_SAMPLES_PER_PIXEL (Config.h:22), default 4. */
+int tpt_set_spp(tpt_context* ctx, int spp);
+/* Implementation knobs (benchmarks/tests): "fast_variant" (0 megakernel, 1/2 persistent), "exact_lanes"
+ * (0 auto, 1, 8, 32), "register_host" (1: cudaHostRegister caller buffers, default 1). */
+int tpt_set_option(tpt_context* ctx, const char* key, int value);
+
+/* Replaces DrawTest() (Test.cpp:344-367) for frames [frameCount, frameCount+numFrames) — numFrames*spp samples
+ * per pixel accumulated with the reference's progressive blend (Test.cpp:272-276,293-295) — over the rows
+ * y_i = row0 + i*rowStep, i in [0,numRows) (TraceRowJob's [start,end) generalised for multi-GPU sharding).
+ *   backbuffer        width*height*4 floats, row 0 = bottom, RGBA; read as `prev` and updated in place exactly like
+ *                     the reference's (Test.cpp:293-296; alpha is preserved). With `packed` != 0 the buffer holds
+ *                     only the numRows rendered rows, back to back.
+ *   bufferOnDevice    0: host pointer (copied in/out inside the call; the call is synchronous like DrawTest)
+ *                     1: device pointer (work is enqueued on `cudaStream`, no host synchronisation unless a ray
+ *                        count is requested)
+ *   outRayCount       NULL or receives the number of rays (every HitWorld call: camera, bounce, shadow —
+ *                     Test.cpp:122,199) of this call; 64-bit because 3840x2160x64 spp exceeds INT_MAX.
+ *   outRaysPerFrame   NULL or numFrames entries (exact mode only; fast mode fills entry 0 with the total).
+ *   cudaStream        a cudaStream_t (NULL = the context's own stream). */
+int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int height,
+             int row0, int numRows, int rowStep, int packed,
+             float* backbuffer, int bufferOnDevice, unsigned testFlags, int mode,
+             long long* outRayCount, long long* outRaysPerFrame, void* cudaStream);
+
+/* Rays traced by all draws since the last call of this function (synchronises the stream). */
+int tpt_read_ray_count(tpt_context* ctx, void* cudaStream, long long* outRays);
+/* Device time (CUDA events on the launching stream) of the kernels of the most recent tpt_draw, in ms. */
+int tpt_last_kernel_ms(tpt_context* ctx, float* outMs);
+/* Number of kernel launches issued by the most recent tpt_draw. */
+int tpt_last_launch_count(tpt_context* ctx);
+
+/* Optional epilogue ("next" row of SURVEY §8f): linear float RGBA -> 8-bit sRGB RGBA with Y flip, the
+ * presentation step of the reference shells (Cpp/Windows/PixelShader.hlsl:1-15). dst = width*height*4 bytes. */
+int tpt_tonemap_srgb8(tpt_context* ctx, const float* image, int imageOnDevice, int width, int height,
+                      unsigned char* dst, int dstOnDevice, void* cudaStream);
+
+/* Diagnostic used by the parity tests: evaluates the device-side libm restatement the exact mode uses
+ * (toypathtracer_b200/csrc/tpt_libm.cuh) on n host floats. fn: 0 = sinf, 1 = cosf, 2 = powf(x, 5). */
+int tpt_debug_libm(tpt_context* ctx, int fn, const float* in, float* out, long long n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

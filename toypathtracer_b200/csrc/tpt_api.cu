@@ -1,0 +1,424 @@
+// C-ABI of include/tpt_b200.h: context, scene upload, draw dispatch, host<->device plumbing.
+// No torch types, no CPU rendering path: every draw ends in a kernel launch or an error.
+#include "../../include/tpt_b200.h"
+#include "tpt_launch.h"
+#include "tpt_scene_pack.h"
+#include "tpt_device_utils.cuh"
+#include "tpt_integrator.cuh"
+#include <string>
+#include <vector>
+#include <string.h>
+#include <stdio.h>
+
+using namespace tpt;
+
+struct tpt_context
+{
+    int device = 0;
+    int numSMs = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    bool haveTiming = false;
+    std::string lastError;
+
+    // scene
+    unsigned char* dBlob = nullptr;
+    size_t blobCap = 0;
+    SceneDev scene{};
+    Camera88 cam{};
+    bool haveScene = false;
+    int spp = 4;
+
+    // options
+    int fastVariant = 1;
+    int exactLanes = 0;
+    int registerHost = 1;
+    size_t maxScratchBytes = (size_t)8 << 30;
+
+    // buffers
+    float* dImage = nullptr; size_t imageCap = 0;      // staging image for host-pointer draws
+    float* dScratch = nullptr; size_t scratchCap = 0;  // exact mode per-frame colours
+    unsigned long long* dRayCounters = nullptr; int rayCounterCap = 0;   // [numFrames]
+    unsigned long long* dAccum = nullptr;              // [0] total since last read, [1] last draw total
+    unsigned int* dWork = nullptr;
+    unsigned long long* hPinned = nullptr; int hPinnedCap = 0;
+    void* registeredPtr = nullptr; size_t registeredBytes = 0;
+    int lastLaunches = 0;
+};
+
+static int fail(tpt_context* ctx, cudaError_t e, const char* what)
+{
+    if (ctx)
+    {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+        ctx->lastError = buf;
+    }
+    return (int)e ? (int)e : -1;
+}
+static int fail_msg(tpt_context* ctx, const char* msg)
+{
+    if (ctx) ctx->lastError = msg;
+    return (int)cudaErrorInvalidValue;
+}
+#define CK(call, what) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(ctx, _e, what); } while (0)
+
+namespace tpt {
+// sums the per-frame counters of one draw into the running totals
+__global__ void k_accumulate_rays(const unsigned long long* perFrame, int n, unsigned long long* accum)
+{
+    unsigned long long s = 0;
+    for (int i = 0; i < n; ++i) s += perFrame[i];
+    accum[0] += s;
+    accum[1] = s;
+}
+
+// LinearToSRGB of the reference's presentation pass (Cpp/Windows/PixelShader.hlsl:1-5) + Y flip (row 0 of the
+// float image is the bottom, Cpp/Emscripten/main.cpp:67-79), 4 bytes per pixel.
+__global__ void k_tonemap_srgb8(const float4* __restrict__ img, int width, int height, uchar4* __restrict__ dst)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= width * height) return;
+    const int x = idx % width, y = idx / width;
+    float4 c = ld_stream_f4(reinterpret_cast<const float*>(img + (size_t)(height - 1 - y) * width + x));
+    auto enc = [](float v) {
+        v = fmaxf(v, 0.0f);
+        v = fmaxf(1.055f * __powf(v, 0.416666667f) - 0.055f, 0.0f);
+        return (unsigned char)(fminf(v, 1.0f) * 255.0f + 0.5f);
+    };
+    dst[idx] = make_uchar4(enc(c.x), enc(c.y), enc(c.z), 255);
+}
+} // namespace tpt
+
+extern "C" {
+
+int tpt_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int tpt_create(int device, tpt_context** out)
+{
+    if (!out) return (int)cudaErrorInvalidValue;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return (int)e;
+    if (n <= 0) return (int)cudaErrorNoDevice;   // no CPU fallback, by design
+    if (device < 0 || device >= n) return (int)cudaErrorInvalidDevice;
+    tpt_context* ctx = new tpt_context();
+    ctx->device = device;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->numSMs, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->evStart);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->evStop);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->dAccum, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ctx->dAccum, 0, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->dWork, 64);
+    if (e != cudaSuccess) { delete ctx; return (int)e; }
+    *out = ctx;
+    return 0;
+}
+
+void tpt_destroy(tpt_context* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->registeredPtr) cudaHostUnregister(ctx->registeredPtr);
+    cudaFree(ctx->dBlob); cudaFree(ctx->dImage); cudaFree(ctx->dScratch); cudaFree(ctx->dRayCounters);
+    cudaFree(ctx->dAccum); cudaFree(ctx->dWork);
+    if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
+    if (ctx->evStart) cudaEventDestroy(ctx->evStart);
+    if (ctx->evStop) cudaEventDestroy(ctx->evStop);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* tpt_last_error(tpt_context* ctx) { return ctx ? ctx->lastError.c_str() : "null context"; }
+
+int tpt_set_scene(tpt_context* ctx, const void* spheres20, const void* materials36, int count,
+                  const void* camera88, const int* emissives, int emissiveCount)
+{
+    if (!ctx) return (int)cudaErrorInvalidValue;
+    if (!spheres20 || !materials36 || !camera88 || count <= 0) return fail_msg(ctx, "tpt_set_scene: bad arguments");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    std::vector<unsigned char> blob;
+    SceneBlobLayout L;
+    int nLights = 0;
+    pack_scene_blob((const Sphere20*)spheres20, (const Material36*)materials36, count, emissives, emissiveCount, blob, L, nLights);
+    // geometry + light table must fit in shared memory next to the kernels' static shared arrays
+    const uint32_t kMaxStage = 200 * 1024;
+    if (L.geomBytes > kMaxStage) return fail_msg(ctx, "tpt_set_scene: too many spheres for shared-memory staging");
+    if (blob.size() > ctx->blobCap)
+    {
+        cudaFree(ctx->dBlob); ctx->dBlob = nullptr; ctx->blobCap = 0;
+        CK(cudaMalloc(&ctx->dBlob, blob.size()), "cudaMalloc scene");
+        ctx->blobCap = blob.size();
+    }
+    // the upload must not race with kernels of a previous draw that still read the old blob
+    CK(cudaStreamSynchronize(ctx->stream), "sync before scene upload");
+    CK(cudaMemcpy(ctx->dBlob, blob.data(), blob.size(), cudaMemcpyHostToDevice), "scene upload");
+    ctx->scene.blob = ctx->dBlob;
+    ctx->scene.layout = L;
+    ctx->scene.count = count;
+    ctx->scene.nLights = nLights;
+    // small scenes: stage everything (spheres + materials); large ones: geometry only, materials from L2
+    ctx->scene.stagedBytes = L.totalBytes <= 64 * 1024 ? L.totalBytes : L.geomBytes;
+    memcpy(&ctx->cam, camera88, sizeof(Camera88));
+    ctx->haveScene = true;
+    return 0;
+}
+
+int tpt_set_camera(tpt_context* ctx, const void* camera88)
+{
+    if (!ctx || !camera88) return (int)cudaErrorInvalidValue;
+    memcpy(&ctx->cam, camera88, sizeof(Camera88));
+    return 0;
+}
+
+int tpt_set_spp(tpt_context* ctx, int spp)
+{
+    if (!ctx) return (int)cudaErrorInvalidValue;
+    if (spp < 1 || spp > 4096) return fail_msg(ctx, "tpt_set_spp: spp out of range");
+    ctx->spp = spp;
+    return 0;
+}
+
+int tpt_set_option(tpt_context* ctx, const char* key, int value)
+{
+    if (!ctx || !key) return (int)cudaErrorInvalidValue;
+    if (!strcmp(key, "fast_variant")) { if (value < 0 || value > 2) return fail_msg(ctx, "fast_variant: 0..2"); ctx->fastVariant = value; return 0; }
+    if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 8 && value != 32) return fail_msg(ctx, "exact_lanes: 0,1,8,32"); ctx->exactLanes = value; return 0; }
+    if (!strcmp(key, "register_host")) { ctx->registerHost = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "max_scratch_mb")) { if (value < 16) return fail_msg(ctx, "max_scratch_mb: >= 16"); ctx->maxScratchBytes = (size_t)value << 20; return 0; }
+    return fail_msg(ctx, "tpt_set_option: unknown key");
+}
+
+static int ensure(tpt_context* ctx, void** p, size_t* cap, size_t bytes, const char* what)
+{
+    if (bytes <= *cap) return 0;
+    CK(cudaStreamSynchronize(ctx->stream), "sync before realloc");
+    cudaFree(*p); *p = nullptr; *cap = 0;
+    CK(cudaMalloc(p, bytes), what);
+    *cap = bytes;
+    return 0;
+}
+
+int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int height,
+             int row0, int numRows, int rowStep, int packed,
+             float* backbuffer, int bufferOnDevice, unsigned testFlags, int mode,
+             long long* outRayCount, long long* outRaysPerFrame, void* cudaStreamArg)
+{
+    if (!ctx) return (int)cudaErrorInvalidValue;
+    if (!ctx->haveScene) return fail_msg(ctx, "tpt_draw: no scene (call tpt_set_scene after UpdateTest)");
+    if (!backbuffer || width <= 0 || height <= 0 || numFrames <= 0 || frameCount < 0 || numRows <= 0 || rowStep <= 0 || row0 < 0)
+        return fail_msg(ctx, "tpt_draw: bad arguments");
+    if (row0 + (long long)(numRows - 1) * rowStep >= height) return fail_msg(ctx, "tpt_draw: rows outside the image");
+    if (mode != TPT_MODE_EXACT && mode != TPT_MODE_FAST) return fail_msg(ctx, "tpt_draw: unknown mode");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t stream = cudaStreamArg ? (cudaStream_t)cudaStreamArg : ctx->stream;
+
+    const size_t bufRows = packed ? (size_t)numRows : (size_t)height;
+    const size_t bufBytes = bufRows * width * 4 * sizeof(float);
+    float* dImage = backbuffer;
+    if (!bufferOnDevice)
+    {
+        int r = ensure(ctx, (void**)&ctx->dImage, &ctx->imageCap, bufBytes, "cudaMalloc image");
+        if (r) return r;
+        dImage = ctx->dImage;
+        if (ctx->registerHost && (ctx->registeredPtr != backbuffer || ctx->registeredBytes != bufBytes))
+        {
+            if (ctx->registeredPtr) { cudaHostUnregister(ctx->registeredPtr); ctx->registeredPtr = nullptr; }
+            // page-lock the caller's buffer once so both copies run at full PCIe rate; failure is not fatal
+            if (cudaHostRegister(backbuffer, bufBytes, cudaHostRegisterDefault) == cudaSuccess)
+            {
+                ctx->registeredPtr = backbuffer; ctx->registeredBytes = bufBytes;
+            }
+            else (void)cudaGetLastError();
+        }
+        // `prev` is an input of the blend (Test.cpp:293). Exact mode always uploads it (NaN/Inf * 0 and the
+        // untouched alpha are part of bit parity). Fast mode uploads it only when prev has a non-zero weight;
+        // otherwise the kernel writes alpha = 0, which is what every reference shell's zero-initialised buffer
+        // holds (TestWin.cpp:73-74, Renderer.mm:148-149, Emscripten/main.cpp:50-51).
+        bool needPrev = mode == TPT_MODE_EXACT;
+        if (!needPrev)
+        {
+            float wPrev = 1.0f;
+            for (int f = 0; f < numFrames; ++f) wPrev *= lerp_fac(frameCount + f, testFlags);
+            needPrev = wPrev != 0.0f;
+        }
+        if (needPrev)
+            CK(cudaMemcpyAsync(dImage, backbuffer, bufBytes, cudaMemcpyHostToDevice, stream), "H2D backbuffer");
+    }
+
+    // frames per launch: exact mode needs numFrames*numRows*width float4 of scratch when numFrames > 1
+    int framesPerLaunch = numFrames;
+    if (mode == TPT_MODE_EXACT && numFrames > 1)
+    {
+        const size_t perFrame = (size_t)numRows * width * 16;
+        size_t fit = ctx->maxScratchBytes / perFrame;
+        if (fit < 1) fit = 1;
+        if ((size_t)framesPerLaunch > fit) framesPerLaunch = (int)fit;
+    }
+    if (mode == TPT_MODE_FAST && framesPerLaunch > 256) framesPerLaunch = 256;
+
+    if (numFrames > ctx->rayCounterCap)
+    {
+        CK(cudaStreamSynchronize(stream), "sync before counter realloc");
+        cudaFree(ctx->dRayCounters); ctx->dRayCounters = nullptr; ctx->rayCounterCap = 0;
+        CK(cudaMalloc(&ctx->dRayCounters, (size_t)numFrames * sizeof(unsigned long long)), "cudaMalloc counters");
+        ctx->rayCounterCap = numFrames;
+    }
+    CK(cudaMemsetAsync(ctx->dRayCounters, 0, (size_t)numFrames * sizeof(unsigned long long), stream), "zero counters");
+
+    DrawParams p;
+    memset(&p, 0, sizeof(p));
+    p.cam = ctx->cam;
+    p.width = width; p.height = height;
+    p.row0 = row0; p.numRows = numRows; p.rowStep = rowStep; p.packed = packed ? 1 : 0;
+    p.spp = ctx->spp;
+    p.flags = testFlags;
+    p.invWidth = 1.0f / (float)width;     // Test.cpp:270-271
+    p.invHeight = 1.0f / (float)height;
+    p.image = dImage;
+    p.workCounter = ctx->dWork;
+
+    ctx->lastLaunches = 0;
+    CK(cudaEventRecord(ctx->evStart, stream), "event record");
+    for (int f = 0; f < numFrames; f += framesPerLaunch)
+    {
+        const int nf = numFrames - f < framesPerLaunch ? numFrames - f : framesPerLaunch;
+        p.frame0 = frameCount + f;
+        p.numFrames = nf;
+        cudaError_t e;
+        if (mode == TPT_MODE_EXACT)
+        {
+            p.rayCounter = ctx->dRayCounters + f;
+            p.scratch = nullptr;
+            if (nf > 1)
+            {
+                int r = ensure(ctx, (void**)&ctx->dScratch, &ctx->scratchCap, (size_t)nf * numRows * width * 16, "cudaMalloc scratch");
+                if (r) return r;
+                p.scratch = ctx->dScratch;
+            }
+            e = launch_exact(p, ctx->scene, ctx->exactLanes, stream);
+            ctx->lastLaunches += nf > 1 ? 2 : 1;
+        }
+        else
+        {
+            p.rayCounter = ctx->dRayCounters;
+            e = launch_fast(p, ctx->scene, ctx->fastVariant, ctx->numSMs, stream);
+            ctx->lastLaunches += fast_kernel_launches(p, ctx->fastVariant);
+        }
+        if (e != cudaSuccess) return fail(ctx, e, "kernel launch");
+    }
+    CK(cudaEventRecord(ctx->evStop, stream), "event record");
+    ctx->haveTiming = true;
+    k_accumulate_rays<<<1, 1, 0, stream>>>(ctx->dRayCounters, numFrames, ctx->dAccum);
+    CK(cudaGetLastError(), "accumulate launch");
+
+    if (!bufferOnDevice)
+        CK(cudaMemcpyAsync(backbuffer, dImage, bufBytes, cudaMemcpyDeviceToHost, stream), "D2H backbuffer");
+
+    if (outRayCount || outRaysPerFrame)
+    {
+        if (numFrames > ctx->hPinnedCap)
+        {
+            if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
+            ctx->hPinned = nullptr; ctx->hPinnedCap = 0;
+            CK(cudaMallocHost(&ctx->hPinned, (size_t)numFrames * sizeof(unsigned long long)), "cudaMallocHost");
+            ctx->hPinnedCap = numFrames;
+        }
+        CK(cudaMemcpyAsync(ctx->hPinned, ctx->dRayCounters, (size_t)numFrames * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "D2H counters");
+        CK(cudaStreamSynchronize(stream), "stream sync");
+        long long total = 0;
+        for (int i = 0; i < numFrames; ++i)
+        {
+            total += (long long)ctx->hPinned[i];
+            if (outRaysPerFrame) outRaysPerFrame[i] = (long long)ctx->hPinned[i];
+        }
+        if (outRayCount) *outRayCount = total;
+    }
+    else if (!bufferOnDevice)
+        CK(cudaStreamSynchronize(stream), "stream sync"); // host-buffer draws are synchronous like DrawTest
+    return 0;
+}
+
+int tpt_read_ray_count(tpt_context* ctx, void* cudaStreamArg, long long* outRays)
+{
+    if (!ctx || !outRays) return (int)cudaErrorInvalidValue;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t stream = cudaStreamArg ? (cudaStream_t)cudaStreamArg : ctx->stream;
+    unsigned long long h[2] = {0, 0};
+    CK(cudaMemcpyAsync(h, ctx->dAccum, sizeof(h), cudaMemcpyDeviceToHost, stream), "D2H accum");
+    CK(cudaMemsetAsync(ctx->dAccum, 0, sizeof(unsigned long long), stream), "reset accum");
+    CK(cudaStreamSynchronize(stream), "stream sync");
+    *outRays = (long long)h[0];
+    return 0;
+}
+
+int tpt_last_kernel_ms(tpt_context* ctx, float* outMs)
+{
+    if (!ctx || !outMs) return (int)cudaErrorInvalidValue;
+    if (!ctx->haveTiming) return fail_msg(ctx, "tpt_last_kernel_ms: no draw yet");
+    CK(cudaEventSynchronize(ctx->evStop), "event sync");
+    CK(cudaEventElapsedTime(outMs, ctx->evStart, ctx->evStop), "event elapsed");
+    return 0;
+}
+
+int tpt_last_launch_count(tpt_context* ctx) { return ctx ? ctx->lastLaunches : 0; }
+
+int tpt_tonemap_srgb8(tpt_context* ctx, const float* image, int imageOnDevice, int width, int height,
+                      unsigned char* dst, int dstOnDevice, void* cudaStreamArg)
+{
+    if (!ctx || !image || !dst || width <= 0 || height <= 0) return (int)cudaErrorInvalidValue;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t stream = cudaStreamArg ? (cudaStream_t)cudaStreamArg : ctx->stream;
+    const size_t inBytes = (size_t)width * height * 16, outBytes = (size_t)width * height * 4;
+    const float* dIn = image;
+    if (!imageOnDevice)
+    {
+        int r = ensure(ctx, (void**)&ctx->dImage, &ctx->imageCap, inBytes, "cudaMalloc image");
+        if (r) return r;
+        CK(cudaMemcpyAsync(ctx->dImage, image, inBytes, cudaMemcpyHostToDevice, stream), "H2D image");
+        dIn = ctx->dImage;
+    }
+    unsigned char* dOut = dst;
+    if (!dstOnDevice)
+    {
+        int r = ensure(ctx, (void**)&ctx->dScratch, &ctx->scratchCap, outBytes, "cudaMalloc tonemap out");
+        if (r) return r;
+        dOut = (unsigned char*)ctx->dScratch;
+    }
+    const int n = width * height;
+    k_tonemap_srgb8<<<(n + 255) / 256, 256, 0, stream>>>((const float4*)dIn, width, height, (uchar4*)dOut);
+    CK(cudaGetLastError(), "tonemap launch");
+    if (!dstOnDevice)
+    {
+        CK(cudaMemcpyAsync(dst, dOut, outBytes, cudaMemcpyDeviceToHost, stream), "D2H tonemap");
+        CK(cudaStreamSynchronize(stream), "stream sync");
+    }
+    return 0;
+}
+
+int tpt_debug_libm(tpt_context* ctx, int fn, const float* in, float* out, long long n)
+{
+    if (!ctx || !in || !out || n <= 0 || fn < 0 || fn > 2) return (int)cudaErrorInvalidValue;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    float *dIn = nullptr, *dOut = nullptr;
+    CK(cudaMalloc(&dIn, (size_t)n * 4), "cudaMalloc");
+    cudaError_t e = cudaMalloc(&dOut, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dIn, in, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = launch_debug_libm(fn, dIn, dOut, n, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dOut, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dIn); cudaFree(dOut);
+    if (e != cudaSuccess) return fail(ctx, e, "tpt_debug_libm");
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,350 @@
+// Fast (throughput) mode kernels: same estimator as the reference's Trace/Scatter (Cpp/Source/Test.cpp:83-234),
+// one independent XorShift32 stream per (pixel, frame) instead of the reference's per-row stream, FMA
+// contraction and fast intrinsics allowed. Results agree with the reference statistically (same expectation,
+// same rays/sample), not bitwise — bitwise parity is the exact mode's job (tpt_exact.cu).
+//
+// variant 0  "megakernel": one thread per pixel, loops over frames x spp (what the reference's own GPU shaders
+//            do, Cpp/Windows/ComputeShader.hlsl:353-395). Baseline for the persistent design.
+// variant 1  "persistent wavefront": one CTA per SM slot, resident for the whole draw. The CTA pulls tiles of
+//            TILE_PIX pixels from a global counter; inside a tile every lane runs a path state machine and
+//            refills itself with the next (pixel, sample) from a warp-aggregated shared counter as soon as its
+//            path ends (ray regeneration), so the ray-vs-all-spheres sweep — 85 % of the instructions — always
+//            runs with full warps. Radiance is accumulated per pixel in shared memory; finished tiles are
+//            written with coalesced 128-bit stores (and 128-bit loads of `prev` when accumulating).
+#include "tpt_integrator.cuh"
+#include "tpt_device_utils.cuh"
+#include "tpt_launch.h"
+
+namespace tpt {
+
+constexpr int kFastThreads = 256;
+constexpr int kTilePix = 1024;          // pixels per tile (12 KB of float3 accumulators)
+constexpr int kMaxFramesPerDraw = 256;  // per-frame blend weights live in shared memory
+
+__device__ __forceinline__ uint32_t fmix32(uint32_t h)
+{
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    return h;
+}
+__device__ __forceinline__ uint32_t pixel_seed(uint32_t pixelIndex, uint32_t frame)
+{
+    return fmix32(pixelIndex * 0x9E3779B9u + fmix32(frame + 0x7F4A7C15u)) | 1u;
+}
+
+// Per-frame weights of the progressive blend (Test.cpp:272-276,293-295) when `numFrames` frames are fused in
+// one launch: image = prev*wPrev + sum_f mean_f * w[f], w[f] = (1-lerp_f) * prod_{g>f} lerp_g.
+__device__ __forceinline__ void blend_weights(const DrawParams& p, float* w, float& wPrev)
+{
+    float suffix = 1.0f;
+    for (int fi = p.numFrames - 1; fi >= 0; --fi)
+    {
+        float lf = lerp_fac(p.frame0 + fi, p.flags);
+        w[fi] = (1.0f - lf) * suffix;
+        suffix *= lf;
+    }
+    wPrev = suffix;
+}
+
+// ---- variant 0 ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFastThreads)
+k_fast_mega(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights, uint32_t stagedBytes)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ float sW[kMaxFramesPerDraw];
+    __shared__ float sWPrev;
+    stage_blob(smem, blob, stagedBytes, &bar);
+    if (threadIdx.x == 0) { float wp; blend_weights(p, sW, wp); sWPrev = wp; }
+    __syncthreads();
+    SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
+
+    // 16x16 pixel block, each warp an 8x4 patch
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tilesX = (p.width + 15) / 16;
+    const int tx = blockIdx.x % tilesX, ty = blockIdx.x / tilesX;
+    const int x = tx * 16 + (warp & 1) * 8 + (lane & 7);
+    const int ri = ty * 16 + (warp >> 1) * 4 + (lane >> 3);
+    unsigned rc = 0;
+    if (x < p.width && ri < p.numRows)
+    {
+        const int y = p.row0 + ri * p.rowStep;
+        SerialHitter<false> hitter;
+        V3 acc = v3(0, 0, 0);
+        const float invSpp = 1.0f / (float)p.spp;
+        for (int fi = 0; fi < p.numFrames; ++fi)
+        {
+            uint32_t state = pixel_seed((uint32_t)(y * p.width + x), (uint32_t)(p.frame0 + fi));
+            V3 col = v3(0, 0, 0);
+            for (int s = 0; s < p.spp; ++s)
+            {
+                float u = ((float)x + RandomFloat01(state)) * p.invWidth;
+                float v = ((float)y + RandomFloat01(state)) * p.invHeight;
+                Ray r = GetRay<false>(p.cam, u, v, state);
+                col = col + trace_fast(sc, r, state, rc, hitter);
+            }
+            acc = acc + col * (invSpp * sW[fi]);
+        }
+        float* px = p.image + ((size_t)(p.packed ? ri : y) * p.width + x) * 4;
+        float4 prev = make_float4(0, 0, 0, 0);
+        const float wPrev = sWPrev;
+        if (wPrev != 0.0f) prev = ld_stream_f4(px);
+        prev.x = prev.x * wPrev + acc.x; prev.y = prev.y * wPrev + acc.y; prev.z = prev.z * wPrev + acc.z;
+        st_stream_f4(px, prev);
+    }
+    // one atomic per warp
+    for (int off = 16; off > 0; off >>= 1) rc += __shfl_xor_sync(0xffffffffu, rc, off);
+    if (lane == 0 && rc) atomicAdd(p.rayCounter, (unsigned long long)rc);
+}
+
+// ---- variant 1 ------------------------------------------------------------------------------------------------
+struct PathState
+{
+    V3 o, d;          // ray to intersect next
+    V3 thr, col;      // throughput before the current vertex, radiance so far
+    V3 nextDir;       // Lambert bounce direction, pending while shadow rays are in flight
+    V3 thrAlb;        // thr * albedo at the pending Lambert vertex
+    V3 nl;            // shading normal facing the incoming ray (Test.cpp:129)
+    V3 pend;          // radiance the in-flight shadow ray carries if it reaches its light
+    V3 albedo;
+    uint32_t rng;
+    int pix;          // pixel index inside the tile
+    float weight;
+    int kind;         // 0: path ray, 1+j: shadow ray towards light j
+    int depth;
+    int mid;          // sphere id of the pending Lambert vertex (skip-self test, Test.cpp:100)
+    bool doMaterialE;
+    bool active;
+};
+
+template <int MINB>
+__global__ void __launch_bounds__(kFastThreads, MINB)
+k_fast_persistent(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights,
+                  uint32_t stagedBytes, int numTiles)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ float sW[kMaxFramesPerDraw];
+    __shared__ float sWPrev;
+    __shared__ float sAcc[kTilePix * 3];
+    __shared__ int sTile;
+    __shared__ int sTask;
+    stage_blob(smem, blob, stagedBytes, &bar);
+    if (threadIdx.x == 0) { float wp; blend_weights(p, sW, wp); sWPrev = wp; }
+    for (int i = threadIdx.x; i < kTilePix * 3; i += kFastThreads) sAcc[i] = 0.0f;
+    SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
+    const int lane = threadIdx.x & 31;
+    const long long regionPix = (long long)p.numRows * p.width;
+    const int S = p.spp * p.numFrames;          // samples per pixel in this draw
+    const float invSpp = 1.0f / (float)p.spp;
+    SerialHitter<false> hitter;
+    unsigned rc = 0;
+
+    for (;;)
+    {
+        __syncthreads(); // sAcc zeroed / previous tile written
+        if (threadIdx.x == 0) { sTile = (int)atomicAdd(p.workCounter, 1u); sTask = 0; }
+        __syncthreads();
+        const int tile = sTile;
+        if (tile >= numTiles) break;
+        const long long pix0 = (long long)tile * kTilePix;
+        const int tilePix = (int)(regionPix - pix0 < kTilePix ? regionPix - pix0 : kTilePix);
+        const int tileTasks = tilePix * S;
+
+        PathState st;
+        st.active = false;
+        for (;;)
+        {
+            // ---- regeneration: lanes without a path take the next (pixel, sample) of the tile
+            unsigned need = __ballot_sync(0xffffffffu, !st.active);
+            if (need)
+            {
+                int base = 0;
+                const int leader = __ffs(need) - 1;
+                if (lane == leader) base = atomicAdd(&sTask, __popc(need));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (!st.active)
+                {
+                    const int task = base + __popc(need & ((1u << lane) - 1u));
+                    if (task < tileTasks)
+                    {
+                        // samples of one pixel sit in adjacent lanes: coherent primary rays
+                        const int pixIn = task / S, sIdx = task % S;
+                        const int fi = sIdx / p.spp;
+                        const long long gp = pix0 + pixIn;
+                        const int ri = (int)(gp / p.width), x = (int)(gp % p.width);
+                        const int y = p.row0 + ri * p.rowStep;
+                        st.rng = pixel_seed((uint32_t)(y * p.width + x) * (uint32_t)p.spp + (uint32_t)(sIdx % p.spp),
+                                            (uint32_t)(p.frame0 + fi));
+                        float u = ((float)x + RandomFloat01(st.rng)) * p.invWidth;
+                        float v = ((float)y + RandomFloat01(st.rng)) * p.invHeight;
+                        Ray r = GetRay<false>(p.cam, u, v, st.rng);
+                        st.o = r.orig; st.d = r.dir;
+                        st.thr = v3(1, 1, 1); st.col = v3(0, 0, 0);
+                        st.pix = pixIn; st.weight = invSpp * sW[fi];
+                        st.kind = 0; st.depth = 0; st.doMaterialE = true; st.active = true;
+                    }
+                }
+            }
+            if (!__any_sync(0xffffffffu, st.active)) break;
+
+            // ---- intersect: every active lane sweeps all spheres (shared-memory broadcast reads)
+            float t = TPT_MAX_T;
+            int id = -1;
+            if (st.active) { id = hitter.hit(sc, st.o, st.d, TPT_MIN_T, TPT_MAX_T, t); ++rc; }
+
+            // ---- shade
+            bool wantLight = false;   // lane must pick its next shadow ray (or resume the path)
+            int lightFrom = 0;
+            bool finished = false;
+            if (st.active)
+            {
+                if (st.kind == 0)
+                {
+                    if (id < 0) { st.col = st.col + st.thr * sky(st.d); finished = true; }
+                    else
+                    {
+                        Q4 s = sc.sph[id];
+                        V3 pos = st.o + st.d * t;
+                        V3 normal = (pos - v3(s.x, s.y, s.z)) * sc.invRadius[id];
+                        const int mid = id < sc.count ? id : sc.count;
+                        Mat mat = load_mat(sc, mid);
+                        if (st.depth >= TPT_MAX_DEPTH) { st.col = st.col + st.thr * mat.emissive; finished = true; }
+                        else if (mat.type == kLambert)
+                        {
+                            if (st.doMaterialE) st.col = st.col + st.thr * mat.emissive;
+                            V3 target = normal + RandomUnitVector<false>(st.rng);
+                            st.nextDir = M<false>::normalize(target);
+                            st.thrAlb = st.thr * mat.albedo;
+                            st.albedo = mat.albedo;
+                            st.nl = dot(normal, st.d) < 0.0f ? normal : neg(normal);
+                            st.mid = mid;
+                            st.o = pos;
+                            wantLight = true; lightFrom = 0;
+                        }
+                        else
+                        {
+                            V3 att, outDir;
+                            bool ok = scatter_specular<false>(mat, st.d, pos, normal, st.rng, att, outDir);
+                            if (!ok) { st.col = st.col + st.thr * mat.emissive; finished = true; }
+                            else
+                            {
+                                if (st.doMaterialE) st.col = st.col + st.thr * mat.emissive;
+                                st.doMaterialE = true;
+                                st.thr = st.thr * att;
+                                st.o = pos; st.d = outDir; ++st.depth;
+                            }
+                        }
+                    }
+                }
+                else
+                {
+                    const int j = st.kind - 1;
+                    if (id == sc.lights[j].id) st.col = st.col + st.pend;
+                    wantLight = true; lightFrom = j + 1;
+                }
+            }
+            // Lambert vertices and returning shadow rays converge here: next light sample or resume the path
+            if (wantLight)
+            {
+                int j = lightFrom;
+                while (j < sc.nLights && sc.lights[j].id == st.mid) ++j;
+                if (j < sc.nLights)
+                {
+                    const LightRec Lr = sc.lights[j];
+                    // sample_light (Test.cpp:104-131) with the facing normal already resolved
+                    V3 scn = v3(Lr.cx, Lr.cy, Lr.cz);
+                    V3 sw = M<false>::normalize(scn - st.o);
+                    V3 su = M<false>::normalize(cross(fabsf(sw.x) > 0.01f ? v3(0, 1, 0) : v3(1, 0, 0), sw));
+                    V3 sv = cross(sw, su);
+                    V3 pc = st.o - scn;
+                    float cosAMax = sqrtf(1.0f - __fdividef(Lr.radius * Lr.radius, dot(pc, pc)));
+                    float eps1 = RandomFloat01(st.rng), eps2 = RandomFloat01(st.rng);
+                    float cosA = 1.0f - eps1 + eps1 * cosAMax;
+                    float sinA = sqrtf(1.0f - cosA * cosA);
+                    float phi = 2.0f * TPT_PI * eps2;
+                    float sp, cp;
+                    __sincosf(phi, &sp, &cp);
+                    V3 l = su * (cp * sinA) + sv * (sp * sinA) + sw * cosA;
+                    float omega = 2.0f * TPT_PI * (1.0f - cosAMax);
+                    float dl = dot(l, st.nl);
+                    float m = (0.0f < dl) ? dl : 0.0f;
+                    st.pend = st.thr * ((st.albedo * v3(Lr.ex, Lr.ey, Lr.ez)) * (m * omega * (1.0f / TPT_PI)));
+                    st.d = l;
+                    st.kind = 1 + j;
+                }
+                else
+                {
+                    st.d = st.nextDir;
+                    st.thr = st.thrAlb;
+                    st.kind = 0;
+                    st.doMaterialE = false;
+                    ++st.depth;
+                }
+            }
+            if (finished)
+            {
+                atomicAdd(&sAcc[st.pix * 3 + 0], st.col.x * st.weight);
+                atomicAdd(&sAcc[st.pix * 3 + 1], st.col.y * st.weight);
+                atomicAdd(&sAcc[st.pix * 3 + 2], st.col.z * st.weight);
+                st.active = false;
+            }
+        }
+
+        // ---- tile done: coalesced 128-bit write-out (+ 128-bit read of prev when accumulating)
+        __syncthreads();
+        const float wPrev = sWPrev;
+        for (int i = threadIdx.x; i < tilePix; i += kFastThreads)
+        {
+            const long long gp = pix0 + i;
+            const int ri = (int)(gp / p.width), x = (int)(gp % p.width);
+            const int y = p.row0 + ri * p.rowStep;
+            float* px = p.image + ((size_t)(p.packed ? ri : y) * p.width + x) * 4;
+            float4 prev = make_float4(0, 0, 0, 0);
+            if (wPrev != 0.0f) prev = ld_stream_f4(px);
+            prev.x = prev.x * wPrev + sAcc[i * 3 + 0];
+            prev.y = prev.y * wPrev + sAcc[i * 3 + 1];
+            prev.z = prev.z * wPrev + sAcc[i * 3 + 2];
+            st_stream_f4(px, prev);
+            sAcc[i * 3 + 0] = 0.0f; sAcc[i * 3 + 1] = 0.0f; sAcc[i * 3 + 2] = 0.0f;
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) rc += __shfl_xor_sync(0xffffffffu, rc, off);
+    if (lane == 0 && rc) atomicAdd(p.rayCounter, (unsigned long long)rc);
+}
+
+int fast_kernel_launches(const DrawParams&, int) { return 1; }
+
+cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, int numSMs, cudaStream_t stream)
+{
+    if (p.numFrames > kMaxFramesPerDraw) return cudaErrorInvalidValue;
+    cudaError_t e;
+    if (variant == 0)
+    {
+        e = cudaFuncSetAttribute(k_fast_mega, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc.stagedBytes);
+        if (e != cudaSuccess) return e;
+        const int tilesX = (p.width + 15) / 16, tilesY = (p.numRows + 15) / 16;
+        k_fast_mega<<<tilesX * tilesY, kFastThreads, sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes);
+        return cudaGetLastError();
+    }
+    if (variant == 1)
+    {
+        auto kern = k_fast_persistent<2>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc.stagedBytes);
+        if (e != cudaSuccess) return e;
+        int perSM = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kFastThreads, sc.stagedBytes);
+        if (e != cudaSuccess) return e;
+        if (perSM < 1) perSM = 1;
+        const long long regionPix = (long long)p.numRows * p.width;
+        const int numTiles = (int)((regionPix + kTilePix - 1) / kTilePix);
+        int grid = numSMs * perSM;
+        if (grid > numTiles) grid = numTiles;
+        e = cudaMemsetAsync(p.workCounter, 0, sizeof(unsigned int), stream);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, kFastThreads, sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes, numTiles);
+        return cudaGetLastError();
+    }
+    return cudaErrorInvalidValue;
+}
+
+} // namespace tpt

@@ -1,0 +1,23 @@
+// Internal interface between the C-ABI (tpt_api.cu) and the two kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include "tpt_types.h"
+
+namespace tpt {
+
+struct SceneDev
+{
+    const unsigned char* blob;   // device copy of the packed scene (tpt_scene_pack.h)
+    SceneBlobLayout layout;
+    int count, nLights;
+    uint32_t stagedBytes;        // prefix of the blob every CTA stages into shared memory via TMA
+};
+
+// lanes: 0 = choose from the number of (frame,row) chains; 1, 8 or 32 to force.
+cudaError_t launch_exact(const DrawParams& p, const SceneDev& sc, int lanes, cudaStream_t stream);
+cudaError_t launch_debug_libm(int fn, const float* dIn, float* dOut, long long n, cudaStream_t stream);
+// variant: see tpt_fast.cu
+cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, int numSMs, cudaStream_t stream);
+int fast_kernel_launches(const DrawParams& p, int variant);
+
+} // namespace tpt

@@ -60,15 +60,17 @@ struct DrawParams
 {
     Camera88 cam;
     int width, height;
-    int row0, numRows;        // row band [row0, row0+numRows)  (Test.cpp:266 TraceRowJob(start,end))
+    int row0, numRows;        // rows y_i = row0 + i*rowStep, i in [0,numRows)  (Test.cpp:266 TraceRowJob(start,end))
+    int rowStep;              // 1 = contiguous band; world_size = rows interleaved across GPUs
+    int packed;               // 0: row y_i lives at image row y_i (full image); 1: at image row i (packed band)
     int frame0, numFrames;    // frames [frame0, frame0+numFrames), N spp = N/spp reference frames
     int spp;                  // DO_SAMPLES_PER_PIXEL (Config.h:22)
     unsigned flags;           // kFlagAnimate = 1, kFlagProgressive = 2 (Test.h:4-8)
     float invWidth, invHeight;
     float* image;             // full image base, width*height*4 floats, row 0 = bottom (device)
     float* scratch;           // exact mode, numFrames > 1: [numFrames][numRows][width] float4 per-frame colours
-    unsigned long long* rayCounter;
-    unsigned int* workCounter; // persistent kernels: next tile
+    unsigned long long* rayCounter; // [numFrames] in exact mode, [1] in fast mode
+    unsigned int* workCounter;      // persistent kernels: next tile
 };
 
 } // namespace tpt
