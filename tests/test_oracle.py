@@ -1,0 +1,100 @@
+"""Pins the oracle: the CPU restatement (oracle/restate.cpp) against the committed golden vectors generated from
+the unmodified reference, and against the reference itself where oracle/_ref/libtoyref.so is present."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import bits_differ
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def golden_scene():
+    g = np.load(os.path.join(GOLD, "scene46_1280x720.npz"))
+    return g["spheres"], g["materials"].view(np.float32), g["camera"], g["emissives"]
+
+
+def scene_for(oracle, w, h):
+    """46-sphere scene at aspect w/h: spheres/materials from the golden export, camera from the reference when
+    available (it depends on the aspect ratio), else only 16:9 sizes are valid."""
+    sph, mats, cam, em = golden_scene()
+    if oracle.have_ref():
+        sph, mats, cam, em = oracle.ref_scene(w, h)
+    else:
+        assert w * 9 == h * 16
+    return sph, mats, cam, em
+
+
+def test_golden_image_and_counts(oracle):
+    g = np.load(os.path.join(GOLD, "ref_192x108_f0-3.npz"))
+    sph, mats, cam, em = golden_scene()
+    buf, rays, pads = oracle.orc_render(sph, mats, cam, 192, 108, 0, 4, flags=2)
+    assert rays == [int(r) for r in g["rays"]]
+    assert not pads
+    assert not bits_differ(buf, g["image"]).any()
+
+
+def test_golden_ray_counts_720p(oracle):
+    counts = json.load(open(os.path.join(GOLD, "ref_counts.json")))
+    sph, mats, cam, em = golden_scene()
+    _, rays, _ = oracle.orc_render(sph, mats, cam, 1280, 720, 0, 2, flags=0)
+    assert rays == counts["1280x720_flags0_frames0-5"][:2]          # 16 809 105, 16 822 947
+
+
+def test_restatement_equals_reference_bitwise(oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/libtoyref.so not built (reference sources absent)")
+    for (w, h, f0, nf, flags) in [(320, 180, 0, 3, 2), (200, 120, 7, 2, 0)]:
+        sph, mats, cam, em = oracle.ref_scene(w, h)
+        rbuf, rrays = oracle.ref_render(w, h, f0, nf, flags=flags)
+        obuf, orays, pads = oracle.orc_render(sph, mats, cam, w, h, f0, nf, flags=flags)
+        assert orays == rrays
+        assert not bits_differ(obuf, rbuf, pads).any()
+
+
+def test_restatement_equals_reference_animated(oracle):
+    """kFlagAnimate: spheres 1 and 8 move with time, lerpFac *= 0.9 (Test.cpp:273-274,304-308)."""
+    if not oracle.have_ref():
+        pytest.skip("needs the reference")
+    w, h, t, flags = 160, 90, 1.25, 3
+    sph, mats, cam, em = oracle.isolated("ref_scene", w, h, time=t, flags=flags)
+    rbuf, rrays = oracle.isolated("ref_render", w, h, 40, 2, flags=flags, time=t)
+    obuf, orays, pads = oracle.orc_render(sph, mats, cam, w, h, 40, 2, flags=flags)
+    assert orays == rrays
+    assert not bits_differ(obuf, rbuf, pads).any()
+
+
+def test_padded_sphere_hit_control_flow(oracle):
+    """Frame 28 of the 1280x720 sequence contains a path ray that 'hits' a padded impossible sphere (reference UB,
+    see oracle/restate.cpp Trace()). The restatement must follow the reference's control flow: equal ray counts,
+    and only that pixel may differ."""
+    if not oracle.have_ref():
+        pytest.skip("needs the reference")
+    sph, mats, cam, em = oracle.ref_scene(1280, 720)
+    rbuf, rrays = oracle.ref_render(1280, 720, 28, 1, flags=0)
+    obuf, orays, pads = oracle.orc_render(sph, mats, cam, 1280, 720, 28, 1, flags=0)
+    assert orays == rrays == [16813074]
+    assert pads == [(180, 436, 28)]
+    assert not bits_differ(obuf, rbuf, pads).any()
+
+
+def test_scalar_vs_simd_tie_rule_agree_on_reference_scene(oracle):
+    sph, mats, cam, em = golden_scene()
+    a, ra, _ = oracle.orc_render(sph, mats, cam, 192, 108, 0, 1, simd_tie=1)
+    b, rb, _ = oracle.orc_render(sph, mats, cam, 192, 108, 0, 1, simd_tie=0)
+    assert ra == rb and not bits_differ(a, b).any()
+
+
+def test_runtime_scene_edge_cases(oracle):
+    """Sizes and scenes the reference itself cannot run: 1 sphere, counts not a multiple of 4, no lights."""
+    import toypathtracer_b200 as tpt
+    cam = tpt.make_camera((0, 1, 4), (0, 0, 0), (0, 1, 0), 45, 2.0, 0.05, 4)
+    for n in (1, 2, 5, 7):
+        sph = np.zeros(n, tpt.SPHERE_DTYPE); mats = np.zeros(n, tpt.MATERIAL_DTYPE)
+        for i in range(n):
+            sph[i] = ((i - n / 2, 0, 0), 0.45, 0)
+            mats[i] = (i % 3, (0.7, 0.6, 0.5), (4, 4, 4) if i == 1 else (0, 0, 0), 0.1, 1.5)
+        buf, rays, pads = oracle.orc_render(sph, mats, cam, 64, 32, 0, 2, flags=2)
+        assert np.isfinite(buf).all() and rays[0] >= 64 * 32 * 4

@@ -1,0 +1,25 @@
+"""Tiny driver for ncu captures: python tools/prof_run.py <mode fast|exact> <variant/lanes> <w> <h> <nframes> <reps> [scene]"""
+import sys, os
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import toypathtracer_b200 as tpt
+import torch
+
+mode, var, w, h, nf, reps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
+scene = sys.argv[7] if len(sys.argv) > 7 else "ref"
+ctx = tpt.Context(0)
+if scene == "ref":
+    sph, mats, cam, em = tpt.reference_scene(w, h)
+else:
+    sph, mats, cam, em = tpt.stress_scene(w, h, int(scene))
+ctx.set_scene(sph, mats, cam, em)
+buf = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+if mode == "fast":
+    ctx.set_option("fast_variant", var)
+    m = tpt.MODE_FAST
+else:
+    ctx.set_option("exact_lanes", var)
+    m = tpt.MODE_EXACT
+for r in range(reps):
+    rays = ctx.draw(r * nf, nf, w, h, buf, flags=0 if nf == 1 else 2, mode=m)
+    print(r, rays, ctx.last_kernel_ms(), "ms", rays / ctx.last_kernel_ms() / 1e3, "Mray/s", flush=True)

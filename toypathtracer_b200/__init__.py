@@ -211,6 +211,7 @@ def _load_shim():
     S._Z14GetObjectCountRiS_S_S_.argtypes = [ctypes.POINTER(ci)] * 4; S._Z14GetObjectCountRiS_S_S_.restype = None
     S._Z12GetSceneDescPvS_S_S_Pi.argtypes = [vp, vp, vp, vp, ctypes.POINTER(ci)]; S._Z12GetSceneDescPvS_S_S_Pi.restype = None
     S.tpt_shim_set_mode.argtypes = [ci]; S.tpt_shim_set_mode.restype = None
+    S.tpt_shim_reset_scene.argtypes = []; S.tpt_shim_reset_scene.restype = None
     _shim = S
     return S
 
@@ -257,6 +258,11 @@ def GetSceneDesc():
     _load_shim()._Z12GetSceneDescPvS_S_S_Pi(spheres.ctypes.data, mats.ctypes.data, cam.ctypes.data, em.ctypes.data,
                                             ctypes.byref(ec))
     return spheres, mats, cam, em[: ec.value].copy()
+
+
+def reset_scene():
+    """Un-animated scene again (UpdateTest with kFlagAnimate moves spheres 1 and 8 permanently, Test.cpp:304-308)."""
+    _load_shim().tpt_shim_reset_scene()
 
 
 def set_mode(mode: int):

@@ -128,6 +128,9 @@ void die(const char* what, int code)
 } // namespace
 
 extern "C" void tpt_shim_set_mode(int mode) { s_Mode = mode; }
+// Restores the un-animated scene (the reference keeps animated positions in its static arrays forever,
+// Test.cpp:304-308; a reference shell never needs this, tests do).
+extern "C" void tpt_shim_reset_scene() { buildScene(); }
 extern "C" tpt_context* tpt_shim_context() { return s_Ctx; }
 
 // Test.cpp:240-246

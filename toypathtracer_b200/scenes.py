@@ -36,9 +36,13 @@ def make_camera(lookfrom, lookat, vup, vfov, aspect, aperture, focus_dist) -> np
 def reference_scene(width: int, height: int, time: float = 0.0, flags: int = 0):
     """(spheres, materials, camera, emissives) of the reference scene at this aspect ratio, produced by the
     drop-in's UpdateTest + GetSceneDesc (host code only; works without a GPU)."""
-    from . import UpdateTest, GetSceneDesc
+    from . import UpdateTest, GetSceneDesc, reset_scene
+    reset_scene()
     UpdateTest(time, 0, width, height, flags)
-    return GetSceneDesc()
+    out = GetSceneDesc()
+    if flags & 1:
+        reset_scene()
+    return out
 
 
 class _XorShift:
