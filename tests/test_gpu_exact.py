@@ -1,0 +1,174 @@
+"""Parity tests proper: the CUDA exact mode, called through the C-ABI / the Test.h drop-in, against the oracle
+and the golden vectors. Bar: bit-identical pixels and identical ray counts (integer work and float work alike —
+the exact mode replays the reference's arithmetic op by op)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import bits_differ
+from test_oracle import GOLD, golden_scene
+
+pytestmark = pytest.mark.gpu
+
+
+def test_device_libm_equals_glibc(gpu_ctx, oracle):
+    """Device sinf/cosf over all 2^24 arguments the path can produce (Maths.cpp:42, Test.cpp:115) and powf(x,5)
+    over 2^24 random bit patterns plus the edge cases, against the libm the reference links."""
+    k = np.arange(1 << 24, dtype=np.uint32)
+    a = (k.astype(np.float32) / np.float32(16777216.0)) * np.float32(2.0) * np.float32(3.1415926)
+    for fn, name in ((0, "sinf"), (1, "cosf")):
+        d = gpu_ctx.debug_libm(fn, a); g = oracle.libm_eval(name, a)
+        assert (d.view(np.uint32) == g.view(np.uint32)).all(), name
+    rng = np.random.default_rng(7)
+    x = rng.integers(0, 1 << 32, 1 << 24, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    edge = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 1.17549435e-38, 3.4e38, 0.5, 2.0 ** -24,
+                     2.0 ** -30, -0.5, 2.5], np.float32)
+    x = np.concatenate([x, edge, np.linspace(-1, 3, 100001, dtype=np.float32)])
+    d = gpu_ctx.debug_libm(2, x); g = oracle.libm_eval("powf", x, 5.0)
+    same = (d.view(np.uint32) == g.view(np.uint32)) | (np.isnan(d) & np.isnan(g))
+    assert same.all()
+
+
+def test_golden_vectors(gpu_ctx):
+    g = np.load(os.path.join(GOLD, "ref_192x108_f0-3.npz"))
+    sph, mats, cam, em = golden_scene()
+    gpu_ctx.set_scene(sph, mats, cam, em)
+    for lanes in (32, 8, 1, 0):
+        gpu_ctx.set_option("exact_lanes", lanes)
+        # frame by frame (numFrames = 1: blend fused into the trace kernel)
+        buf = np.zeros((108, 192, 4), np.float32)
+        rays = [gpu_ctx.draw(f, 1, 192, 108, buf, flags=2, mode=0) for f in range(4)]
+        assert rays == [int(r) for r in g["rays"]]
+        assert not bits_differ(buf, g["image"]).any()
+        # one call for the 4 frames (scratch + resolve kernel)
+        buf = np.zeros((108, 192, 4), np.float32)
+        total, per_frame = gpu_ctx.draw(0, 4, 192, 108, buf, flags=2, mode=0, per_frame=True)
+        assert per_frame == [int(r) for r in g["rays"]] and total == int(g["rays"].sum())
+        assert not bits_differ(buf, g["image"]).any()
+    gpu_ctx.set_option("exact_lanes", 0)
+
+
+def test_dropin_drawtest_full_size_vs_golden_counts_and_reference(libs, oracle):
+    """The BASELINE configuration (46 spheres, 1280x720, 4 spp) through the drop-in's UpdateTest/DrawTest."""
+    counts = json.load(open(os.path.join(GOLD, "ref_counts.json")))["1280x720_flags0_frames0-5"]
+    w, h = 1280, 720
+    libs.reset_scene()
+    libs.InitializeTest()
+    libs.set_mode(libs.MODE_EXACT)
+    buf = np.zeros((h, w, 4), np.float32)
+    rays = []
+    for f in range(3):
+        libs.UpdateTest(0.0, f, w, h, 0)
+        rays.append(libs.DrawTest(0.0, f, w, h, buf, 0))
+    assert rays == counts[:3]                                    # 16 809 105 / 16 822 947 / 16 818 090
+    assert (buf[..., 3] == 0).all()                              # alpha untouched (Maths.h:38)
+    if oracle.have_ref():
+        rbuf, rrays = oracle.ref_render(w, h, 0, 3, flags=0)
+        assert rrays == rays
+        assert not bits_differ(buf, rbuf).any()
+    libs.ShutdownTest()
+
+
+def test_progressive_prev_semantics(gpu_ctx, oracle):
+    """`prev` is an input: non-zero, NaN and Inf pixels, alpha preserved (Test.cpp:293-295)."""
+    sph, mats, cam, em = golden_scene()
+    gpu_ctx.set_scene(sph, mats, cam, em)
+    w, h = 192, 108
+    rng = np.random.default_rng(3)
+    init = rng.random((h, w, 4), dtype=np.float32)
+    init[5, 7, 0] = np.nan; init[6, 8, 1] = np.inf; init[:, :, 3] = 0.75
+    for flags in (0, 2):
+        a = init.copy(); b = init.copy()
+        obuf, orays, pads = oracle.orc_render(sph, mats, cam, w, h, 3, 2, flags=flags, buf=a)
+        rays = gpu_ctx.draw(3, 1, w, h, b, flags=flags, mode=0) + gpu_ctx.draw(4, 1, w, h, b, flags=flags, mode=0)
+        assert rays == sum(orays)
+        assert not bits_differ(b, obuf, pads).any()
+        assert (b[..., 3] == np.float32(0.75)).all()
+        c = init.copy()
+        gpu_ctx.draw(3, 2, w, h, c, flags=flags, mode=0)
+        assert not bits_differ(c, obuf, pads).any()
+
+
+def test_row_sharding_is_exact(gpu_ctx):
+    """Rows are independent units (Test.cpp:278-280): any band / interleave of rows reproduces the same pixels."""
+    sph, mats, cam, em = golden_scene()
+    gpu_ctx.set_scene(sph, mats, cam, em)
+    w, h = 192, 108
+    full = np.zeros((h, w, 4), np.float32)
+    total = gpu_ctx.draw(0, 2, w, h, full, flags=2, mode=0)
+    # two contiguous bands into the full image
+    img = np.zeros((h, w, 4), np.float32)
+    r = gpu_ctx.draw(0, 2, w, h, img, flags=2, mode=0, rows=(0, 50, 1, 0)) + \
+        gpu_ctx.draw(0, 2, w, h, img, flags=2, mode=0, rows=(50, 58, 1, 0))
+    assert r == total and not bits_differ(img, full).any()
+    # 4-way interleave, packed bands (what the multi-GPU path does per rank)
+    img = np.zeros((h, w, 4), np.float32)
+    r = 0
+    for rank in range(4):
+        band = np.zeros((h // 4, w, 4), np.float32)
+        r += gpu_ctx.draw(0, 2, w, h, band, flags=2, mode=0, rows=(rank, h // 4, 4, 1))
+        img[rank::4] = band
+    assert r == total and not bits_differ(img, full).any()
+
+
+def test_animated_scene(libs, gpu_ctx, oracle):
+    sph, mats, cam, em = libs.reference_scene(320, 180, time=2.5, flags=3)
+    gpu_ctx.set_scene(sph, mats, cam, em)
+    obuf, orays, pads = oracle.orc_render(sph, mats, cam, 320, 180, 10, 3, flags=3)
+    buf = np.zeros((180, 320, 4), np.float32)
+    total, pf = gpu_ctx.draw(10, 3, 320, 180, buf, flags=3, mode=0, per_frame=True)
+    assert pf == orays and not bits_differ(buf, obuf, pads).any()
+
+
+def test_runtime_scenes_against_restatement(libs, gpu_ctx, oracle):
+    """Scenes the reference cannot run (static array, Test.cpp:13-64): counts that are / are not multiples of 4,
+    a single sphere, no lights, many lights, the 4096-sphere stress scene (BASELINE configs[4]) at a small size."""
+    cases = []
+    cam = libs.make_camera((0, 1, 4), (0, 0, 0), (0, 1, 0), 45, 2.0, 0.05, 4)
+    for n in (1, 2, 5, 7):
+        sph = np.zeros(n, libs.SPHERE_DTYPE); mats = np.zeros(n, libs.MATERIAL_DTYPE)
+        for i in range(n):
+            sph[i] = ((i - n / 2, 0, 0), 0.45, 0)
+            mats[i] = (i % 3, (0.7, 0.6, 0.5), (4, 4, 4) if i == 1 else (0, 0, 0), 0.1, 1.5)
+        cases.append((sph, mats, cam, 64, 32))
+    s203 = libs.stress_scene(160, 90, count=203)
+    cases.append((s203[0], s203[1], s203[2], 160, 90))
+    s4096 = libs.stress_scene(96, 54, count=4096)
+    cases.append((s4096[0], s4096[1], s4096[2], 96, 54))
+    for (sph, mats, cam, w, h) in cases:
+        gpu_ctx.set_scene(sph, mats, cam, None)
+        obuf, orays, pads = oracle.orc_render(sph, mats, cam, w, h, 0, 2, flags=2)
+        for lanes in (32, 1):
+            gpu_ctx.set_option("exact_lanes", lanes)
+            buf = np.zeros((h, w, 4), np.float32)
+            total, pf = gpu_ctx.draw(0, 2, w, h, buf, flags=2, mode=0, per_frame=True)
+            assert pf == orays, (len(sph), lanes)
+            assert not bits_differ(buf, obuf, pads).any(), (len(sph), lanes)
+    gpu_ctx.set_option("exact_lanes", 0)
+
+
+def test_padded_sphere_hit_frame(gpu_ctx, oracle):
+    """Frame 28 at 1280x720 holds a ray that hits a padded impossible sphere (reference UB): ray counts must still
+    equal the reference's, and every pixel except that one must be bit-identical."""
+    sph, mats, cam, em = golden_scene()
+    gpu_ctx.set_scene(sph, mats, cam, em)
+    buf = np.zeros((720, 1280, 4), np.float32)
+    rays = gpu_ctx.draw(28, 1, 1280, 720, buf, flags=0, mode=0)
+    assert rays == 16813074
+    if oracle.have_ref():
+        rbuf, rrays = oracle.ref_render(1280, 720, 28, 1, flags=0)
+        assert rrays == [rays]
+        assert not bits_differ(buf, rbuf, [(180, 436, 28)]).any()
+
+
+def test_4k_frame_ray_count(gpu_ctx, libs):
+    """3840x2160 frame 0 = 151 330 258 rays (golden)."""
+    counts = json.load(open(os.path.join(GOLD, "ref_counts.json")))
+    sph, mats, cam, em = libs.reference_scene(3840, 2160)
+    gpu_ctx.set_scene(sph, mats, cam, em)
+    import torch
+    buf = torch.zeros((2160, 3840, 4), dtype=torch.float32, device="cuda")
+    rays = gpu_ctx.draw(0, 1, 3840, 2160, buf, flags=0, mode=0)
+    assert [rays] == counts["3840x2160_flags0_frame0"]

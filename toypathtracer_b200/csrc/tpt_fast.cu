@@ -203,7 +203,7 @@ k_fast_persistent(DrawParams p, const unsigned char* __restrict__ blob, SceneBlo
                     if (id < 0) { st.col = st.col + st.thr * sky(st.d); finished = true; }
                     else
                     {
-                        Q4 s = sc.sph[id];
+                        Q4 s = ld_sph(sc, id);
                         V3 pos = st.o + st.d * t;
                         V3 normal = (pos - v3(s.x, s.y, s.z)) * sc.invRadius[id];
                         const int mid = id < sc.count ? id : sc.count;
@@ -257,10 +257,10 @@ k_fast_persistent(DrawParams p, const unsigned char* __restrict__ blob, SceneBlo
                     V3 su = M<false>::normalize(cross(fabsf(sw.x) > 0.01f ? v3(0, 1, 0) : v3(1, 0, 0), sw));
                     V3 sv = cross(sw, su);
                     V3 pc = st.o - scn;
-                    float cosAMax = sqrtf(1.0f - __fdividef(Lr.radius * Lr.radius, dot(pc, pc)));
+                    float cosAMax = M<false>::sqrt_(1.0f - __fdividef(Lr.radius * Lr.radius, dot(pc, pc)));
                     float eps1 = RandomFloat01(st.rng), eps2 = RandomFloat01(st.rng);
                     float cosA = 1.0f - eps1 + eps1 * cosAMax;
-                    float sinA = sqrtf(1.0f - cosA * cosA);
+                    float sinA = M<false>::sqrt_(1.0f - cosA * cosA);
                     float phi = 2.0f * TPT_PI * eps2;
                     float sp, cp;
                     __sincosf(phi, &sp, &cp);
@@ -326,9 +326,9 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
         k_fast_mega<<<tilesX * tilesY, kFastThreads, sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes);
         return cudaGetLastError();
     }
-    if (variant == 1)
+    if (variant == 1 || variant == 2)
     {
-        auto kern = k_fast_persistent<2>;
+        auto kern = variant == 1 ? k_fast_persistent<2> : k_fast_persistent<3>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc.stagedBytes);
         if (e != cudaSuccess) return e;
         int perSM = 0;

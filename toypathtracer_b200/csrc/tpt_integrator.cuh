@@ -50,7 +50,10 @@ template <bool EXACT> struct M
     static TPT_HD float sqrt_(float x)
     {
 #if defined(__CUDA_ARCH__)
-        return EXACT ? __fsqrt_rn(x) : sqrtf(x);
+        if (EXACT) return __fsqrt_rn(x);
+        float r;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
 #else
         return sqrtf(x);
 #endif
@@ -192,14 +195,78 @@ template <bool EXACT> TPT_HD void test_sphere(const Q4 s, int i, V3 o, V3 d, flo
     }
 }
 
-// Every lane sweeps all spheres itself (lane = ray).
+// sph[i] = {cx, cy, cz, r^2}. On the device the array always lives in shared memory (staged by TMA): read it
+// with ld.shared.v4 (LDS.128; all lanes of a warp read the same address in the sweep -> broadcast).
+TPT_HD Q4 ld_sph(const SceneView& sc, int i)
+{
+#if defined(__CUDA_ARCH__)
+    Q4 r;
+    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(sc.sphShared + (uint32_t)i * 16u));
+    return r;
+#else
+    return sc.sph[i];
+#endif
+}
+
+// Maths.cpp:97-102 / 171-176: the discriminant of one ray-sphere pair (shared by both passes below).
+TPT_HD float sphere_discr(const Q4 s, V3 o, V3 d, float& nb)
+{
+    float coX = s.x - o.x;
+    float coY = s.y - o.y;
+    float coZ = s.z - o.z;
+    nb = coX * d.x + coY * d.y + coZ * d.z;
+    float c = coX * coX + coY * coY + coZ * coZ - s.w;
+    return nb * nb - c;
+}
+
+// Every lane sweeps all spheres itself (lane = ray), in two passes per chunk of 32 spheres:
+//   pass 1  branch-free, fully unrolled: discriminant of every sphere, sign collected in a 32-bit candidate mask
+//           (10 FP32 ops + compare + predicated OR per sphere, independent across spheres);
+//   pass 2  only the few spheres whose line the ray crosses (discr > 0): sqrt, root selection, nearest-hit
+//           update. Each lane walks ITS OWN candidates, so a warp pays max-over-lanes candidates, not the union.
+// Per sphere the arithmetic is exactly test_sphere()'s and the winner is chosen under the same total order, so
+// the result is identical to the plain loop (and to Maths.cpp:165-202 + the SSE tie rule).
 template <bool EXACT> struct SerialHitter
 {
     TPT_HD int hit(const SceneView& sc, V3 o, V3 d, float tMin, float tMax, float& tOut) const
     {
         float bestT = tMax;
         int bestId = -1;
-        for (int i = 0; i < sc.simdCount; ++i) test_sphere<EXACT>(sc.sph[i], i, o, d, tMin, bestT, bestId);
+        for (int base = 0; base < sc.simdCount; base += 32)
+        {
+            const int n = sc.simdCount - base < 32 ? sc.simdCount - base : 32;   // multiple of 4
+            uint32_t cand = 0;
+#pragma unroll
+            for (int k = 0; k < 32; k += 4)
+            {
+                if (k < n)
+                {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                    {
+                        float nb;
+                        float discr = sphere_discr(ld_sph(sc, base + k + j), o, d, nb);
+                        if (discr > 0.0f) cand |= 1u << (k + j);
+                    }
+                }
+            }
+            while (cand)
+            {
+#if defined(__CUDA_ARCH__)
+                const int k = __ffs((int)cand) - 1;
+#else
+                const int k = __builtin_ctz(cand);
+#endif
+                cand &= cand - 1;
+                const int i = base + k;
+                float nb;
+                float discr = sphere_discr(ld_sph(sc, i), o, d, nb);
+                float discrSq = M<EXACT>::sqrt_(discr);
+                float t = nb - discrSq;
+                if (t <= tMin) t = nb + discrSq;
+                if (t > tMin && hit_better(t, i, bestT, bestId)) { bestT = t; bestId = i; }
+            }
+        }
         tOut = bestT;
         return bestId;
     }
@@ -216,7 +283,7 @@ template <bool EXACT, int LANES> struct GroupHitter
     {
         float bestT = tMax;
         int bestId = -1;
-        for (int i = sub; i < sc.simdCount; i += LANES) test_sphere<EXACT>(sc.sph[i], i, o, d, tMin, bestT, bestId);
+        for (int i = sub; i < sc.simdCount; i += LANES) test_sphere<EXACT>(ld_sph(sc, i), i, o, d, tMin, bestT, bestId);
 #pragma unroll
         for (int off = LANES / 2; off > 0; off >>= 1)
         {
@@ -360,7 +427,7 @@ TPT_HD V3 trace_exact(const SceneView& sc, Ray r, uint32_t& state, unsigned& ray
         int id = hitter.hit(sc, r.orig, r.dir, TPT_MIN_T, TPT_MAX_T, t);
         if (id < 0) { result = sky(r.dir); break; }
         // Maths.cpp:156-157 / 195-196
-        Q4 s = sc.sph[id];
+        Q4 s = ld_sph(sc, id);
         V3 pos = r.orig + r.dir * t;
         V3 normal = (pos - v3(s.x, s.y, s.z)) * sc.invRadius[id];
         // id >= count: a padded "impossible" sphere was hit; the reference reads s_SphereMats out of bounds
@@ -417,7 +484,7 @@ TPT_HD V3 trace_fast(const SceneView& sc, Ray r, uint32_t& state, unsigned& rayC
         float t;
         int id = hitter.hit(sc, r.orig, r.dir, TPT_MIN_T, TPT_MAX_T, t);
         if (id < 0) { col = col + thr * sky(r.dir); break; }
-        Q4 s = sc.sph[id];
+        Q4 s = ld_sph(sc, id);
         V3 pos = r.orig + r.dir * t;
         V3 normal = (pos - v3(s.x, s.y, s.z)) * sc.invRadius[id];
         int mid = id < sc.count ? id : sc.count;

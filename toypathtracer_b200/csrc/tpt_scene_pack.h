@@ -93,6 +93,7 @@ inline SceneView scene_view_from_blob(const unsigned char* base, const SceneBlob
     v.count = count;
     v.simdCount = (count + 3) / 4 * 4;
     v.nLights = nLights;
+    v.sphShared = 0;
     return v;
 }
 

@@ -45,6 +45,7 @@ struct SceneView
     const float* matRi;
     const LightRec* lights;
     int count, simdCount, nLights;
+    uint32_t sphShared;   // device: 32-bit shared-memory address of sph[] (always staged), for ld.shared.v4
 };
 
 // Blob layout in global memory (one contiguous, 16 B-aligned allocation so a single bulk copy stages it
