@@ -52,7 +52,9 @@ int tpt_set_camera(tpt_context* ctx, const void* camera88);
 /* DO_SAMPLES_PER_PIXEL (Config.h:22), default 4. */
 int tpt_set_spp(tpt_context* ctx, int spp);
 /* Implementation knobs (benchmarks/tests): "fast_variant" (0 megakernel, 1/2 persistent), "exact_lanes"
- * (0 auto, 1, 8, 32), "register_host" (1: cudaHostRegister caller buffers, default 1). */
+ * (0 auto, 1, 8, 32), "register_host" (1: page-lock the caller's host backbuffer with cudaHostRegister the first
+ * time it is seen so both copies run at full PCIe rate; only safe when the buffer outlives the context, as a
+ * reference shell's does; default 0 — buffers that are already pinned are detected by CUDA on their own). */
 int tpt_set_option(tpt_context* ctx, const char* key, int value);
 
 /* Replaces DrawTest() (Test.cpp:344-367) for frames [frameCount, frameCount+numFrames) — numFrames*spp samples

@@ -67,7 +67,10 @@ def gpu_ctx(libs):
 
 def bits_differ(a, b, exclude=()):
     """Boolean [h,w] map of pixels whose RGBA bits differ, minus (x, y[, frame]) pixels in `exclude`."""
-    d = (np.ascontiguousarray(a).view(np.uint32) != np.ascontiguousarray(b).view(np.uint32)).any(axis=2)
+    a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
+    # NaN payload/sign propagation is not specified by IEEE 754 (x86 keeps the operand's payload, the GPU emits
+    # the canonical NaN): a NaN matches a NaN, everything else is compared bit for bit.
+    d = ((a.view(np.uint32) != b.view(np.uint32)) & ~(np.isnan(a) & np.isnan(b))).any(axis=2)
     for p in exclude:
         d[p[1], p[0]] = False
     return d

@@ -5,7 +5,8 @@
 // DrawTest forwards to the CUDA kernels through the C-ABI (include/tpt_b200.h). No tracing happens on the CPU.
 //
 // Extra C entry points (not in Test.h) select the mode/device: tpt_shim_set_mode(), tpt_shim_context().
-// Environment: TPT_MODE=exact|fast (default exact: results bit-identical to the reference), TPT_DEVICE=<n>.
+// Environment: TPT_MODE=exact|fast (default exact: results bit-identical to the reference), TPT_DEVICE=<n>,
+// TPT_PIN_BACKBUFFER=1 (cudaHostRegister the caller's backbuffer once).
 #include "../../include/tpt_b200.h"
 #include <math.h>
 #include <stdint.h>
@@ -144,6 +145,10 @@ void InitializeTest()
     const char* d = getenv("TPT_DEVICE");
     int rc = tpt_create(d ? atoi(d) : 0, &s_Ctx);
     if (rc) die("tpt_create", rc);
+    // A shell's backbuffer lives as long as the app (TestWin.cpp:73, Renderer.mm:148): page-locking it once lets
+    // the per-frame copies run at full PCIe rate. Opt-in because the buffer must outlive the context.
+    const char* pin = getenv("TPT_PIN_BACKBUFFER");
+    if (pin && atoi(pin)) tpt_set_option(s_Ctx, "register_host", 1);
 }
 
 // Test.cpp:248-253

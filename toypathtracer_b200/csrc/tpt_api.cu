@@ -32,7 +32,7 @@ struct tpt_context
     // options
     int fastVariant = 1;
     int exactLanes = 0;
-    int registerHost = 1;
+    int registerHost = 0;
     size_t maxScratchBytes = (size_t)8 << 30;
 
     // buffers
