@@ -61,7 +61,7 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -148,7 +148,7 @@ def cpu_baseline_sample():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
@@ -186,7 +186,8 @@ def main():
     # flags = 0 exactly like the reference step; at N > 1 rank r renders global frame s*N + r.
     image = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)          # a real (non-NULL) stream: the library treats NULL as "my own stream"
+    torch.cuda.set_stream(stream)
     sh = stream.cuda_stream
 
     def step(s, timed_events=None):
@@ -281,7 +282,7 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": None, "peak_source": peak_src,
-                         "kernel": "k_fast_persistent" if args.mode == "fast" else "k_trace_exact",
+                         "kernel": "k_fast_queue" if args.mode == "fast" else "k_trace_exact",
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "the path is FP32-issue bound, not HBM bound (SURVEY §8d): 16 B/pixel written per launch; "
                                  "see fp32 for the binding roofline",

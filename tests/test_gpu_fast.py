@@ -10,7 +10,7 @@ from test_oracle import golden_scene
 pytestmark = pytest.mark.gpu
 
 W, H = 640, 360
-VARIANTS = (0, 1, 2)
+VARIANTS = (0, 1, 3, 4)
 
 
 @pytest.fixture(scope="module")
@@ -65,7 +65,7 @@ def test_variants_and_sharding_consistent(gpu_ctx):
     the pixel, not on which rank/launch renders it (variant 1)."""
     sph, mats, cam, em = golden_scene()
     gpu_ctx.set_scene(sph, mats, cam, em)
-    gpu_ctx.set_option("fast_variant", 1)
+    gpu_ctx.set_option("fast_variant", 3)
     full = np.zeros((H, W, 4), np.float32)
     total = gpu_ctx.draw(0, 2, W, H, full, flags=2, mode=1)
     img = np.zeros((H, W, 4), np.float32)
@@ -81,7 +81,7 @@ def test_variants_and_sharding_consistent(gpu_ctx):
 def test_progressive_accumulation_matches_single_call(gpu_ctx):
     sph, mats, cam, em = golden_scene()
     gpu_ctx.set_scene(sph, mats, cam, em)
-    gpu_ctx.set_option("fast_variant", 1)
+    gpu_ctx.set_option("fast_variant", 3)
     one = np.zeros((H, W, 4), np.float32)
     gpu_ctx.draw(0, 8, W, H, one, flags=2, mode=1)
     seq = np.zeros((H, W, 4), np.float32)

@@ -51,7 +51,7 @@ ctx.set_option("exact_lanes", 0)
 # fast variants
 import torch
 dbuf = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
-for var in (0, 1, 2):
+for var in (0, 1, 2, 3, 4):
     ctx.set_option("fast_variant", var)
     for rep in range(3):
         rays = ctx.draw(rep, 1, w, h, dbuf, flags=0, mode=tpt.MODE_FAST)
@@ -59,7 +59,7 @@ for var in (0, 1, 2):
     img = dbuf.cpu().numpy()
     log(f"fast variant={var}: rays {rays} rays/sample {rays/(w*h*4):.4f} kernel ms {ms:.3f} -> {rays/ms/1e3:.1f} Mray/s  mean {img[...,:3].mean(axis=(0,1))} ref mean {rbuf[...,:3].mean(axis=(0,1))}")
 # fast 64 spp accumulate vs ref 64 spp
-for var in (0, 1):
+for var in (0, 1, 3):
     ctx.set_option("fast_variant", var)
     dbuf.zero_()
     rays = ctx.draw(0, 16, w, h, dbuf, flags=2, mode=tpt.MODE_FAST)

@@ -3,7 +3,6 @@ import sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import toypathtracer_b200 as tpt
-import torch
 
 mode, var, w, h, nf, reps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
 scene = sys.argv[7] if len(sys.argv) > 7 else "ref"
@@ -13,7 +12,7 @@ if scene == "ref":
 else:
     sph, mats, cam, em = tpt.stress_scene(w, h, int(scene))
 ctx.set_scene(sph, mats, cam, em)
-buf = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+buf = np.zeros((h, w, 4), np.float32)
 if mode == "fast":
     ctx.set_option("fast_variant", var)
     m = tpt.MODE_FAST

@@ -30,7 +30,7 @@ struct tpt_context
     int spp = 4;
 
     // options
-    int fastVariant = 1;
+    int fastVariant = 3;
     int exactLanes = 0;
     int registerHost = 0;
     size_t maxScratchBytes = (size_t)8 << 30;
@@ -191,7 +191,7 @@ int tpt_set_spp(tpt_context* ctx, int spp)
 int tpt_set_option(tpt_context* ctx, const char* key, int value)
 {
     if (!ctx || !key) return (int)cudaErrorInvalidValue;
-    if (!strcmp(key, "fast_variant")) { if (value < 0 || value > 2) return fail_msg(ctx, "fast_variant: 0..2"); ctx->fastVariant = value; return 0; }
+    if (!strcmp(key, "fast_variant")) { if (value < 0 || value > 4) return fail_msg(ctx, "fast_variant: 0..4"); ctx->fastVariant = value; return 0; }
     if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 8 && value != 32) return fail_msg(ctx, "exact_lanes: 0,1,8,32"); ctx->exactLanes = value; return 0; }
     if (!strcmp(key, "register_host")) { ctx->registerHost = value ? 1 : 0; return 0; }
     if (!strcmp(key, "max_scratch_mb")) { if (value < 16) return fail_msg(ctx, "max_scratch_mb: >= 16"); ctx->maxScratchBytes = (size_t)value << 20; return 0; }

@@ -312,7 +312,255 @@ k_fast_persistent(DrawParams p, const unsigned char* __restrict__ blob, SceneBlo
     if (lane == 0 && rc) atomicAdd(p.rayCounter, (unsigned long long)rc);
 }
 
-int fast_kernel_launches(const DrawParams&, int) { return 1; }
+
+// ---- variant 3 ------------------------------------------------------------------------------------------------
+// "persistent queue": no tiles, no block barriers after the prologue. Every WARP pulls slabs of kSlabPix pixels x
+// one sample index from a global counter (one atomic per 128 paths), deals the slab's paths to its idle lanes
+// (ray regeneration, no atomics inside the warp: the slab cursor is warp-uniform), and every finished path adds
+// its weighted radiance to the float4 accumulation buffer with ONE 128-bit vector reduction
+// (red.global.add.v4.f32, SASS REDG.E.ADD.F32x4) that resolves in L2. A tiny prepare kernel first scales the
+// buffer by the weight of `prev` (or zeroes it). End-of-kernel tail = one slab per warp instead of one 1024-pixel
+// tile per CTA, which matters at 1280x720x4spp where a warp's share of the whole frame is only ~1000 paths.
+constexpr int kSlabPix = 128;
+constexpr int kQueueThreads = 128;
+
+__global__ void k_prepare_image(DrawParams p, float wPrev)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)p.numRows * p.width;
+    if (idx >= n) return;
+    const int ri = (int)(idx / p.width), x = (int)(idx % p.width);
+    const int y = p.row0 + ri * p.rowStep;
+    float* px = p.image + ((size_t)(p.packed ? ri : y) * p.width + x) * 4;
+    float4 v = make_float4(0, 0, 0, 0);
+    if (wPrev != 0.0f)
+    {
+        v = ld_stream_f4(px);
+        v.x *= wPrev; v.y *= wPrev; v.z *= wPrev;
+    }
+    *reinterpret_cast<float4*>(px) = v;   // stays in L2 for the reductions that follow
+}
+
+__device__ __forceinline__ void red_add_f4(float* addr, float x, float y, float z)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(0.0f) : "memory");
+}
+
+struct QPath
+{
+    V3 o, d;
+    V3 thr, col;
+    V3 nextDir;
+    V3 thrAlb;
+    V3 nl;
+    V3 pend;
+    V3 albedo;
+    uint32_t rng;
+    uint32_t pixOff;  // float4 index of the pixel in the image buffer
+    float weight;
+    int kind;
+    int depth;
+    int mid;
+    bool doMaterialE;
+    bool active;
+};
+
+template <int MINB>
+__global__ void __launch_bounds__(kQueueThreads, MINB)
+k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights,
+             uint32_t stagedBytes, uint32_t numSlabs, uint32_t S)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ float sW[kMaxFramesPerDraw];
+    stage_blob(smem, blob, stagedBytes, &bar);
+    if (threadIdx.x == 0) { float wp; blend_weights(p, sW, wp); }
+    __syncthreads();
+    SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
+    const int lane = threadIdx.x & 31;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const uint32_t regionPix = (uint32_t)((long long)p.numRows * p.width);
+    const float invSpp = 1.0f / (float)p.spp;
+    SerialHitter<false> hitter;
+    unsigned rc = 0;
+
+    // warp-uniform slab cursor
+    uint32_t slabCur = 0, slabEnd = 0;
+    int slabX0 = 0, slabRi0 = 0;
+    uint32_t slabSample = 0, slabFrame = 0;
+    float slabW = 0.0f;
+    bool exhausted = false;
+
+    QPath st;
+    st.active = false;
+    for (;;)
+    {
+        // ---- regeneration
+        unsigned need = __ballot_sync(0xffffffffu, !st.active);
+        while (need && !exhausted)
+        {
+            if (slabCur >= slabEnd)
+            {
+                uint32_t slab = 0;
+                if (lane == 0) slab = atomicAdd(p.workCounter, 1u);
+                slab = __shfl_sync(0xffffffffu, slab, 0);
+                if (slab >= numSlabs) { exhausted = true; break; }
+                const uint32_t mtile = slab / S, s = slab - mtile * S;
+                const uint32_t pix0 = mtile * kSlabPix;
+                slabEnd = regionPix - pix0 < (uint32_t)kSlabPix ? regionPix - pix0 : (uint32_t)kSlabPix;
+                slabCur = 0;
+                slabRi0 = (int)(pix0 / (uint32_t)p.width);
+                slabX0 = (int)(pix0 - (uint32_t)slabRi0 * (uint32_t)p.width);
+                const uint32_t fi = s / (uint32_t)p.spp;
+                slabSample = s - fi * (uint32_t)p.spp;
+                slabFrame = (uint32_t)p.frame0 + fi;
+                slabW = invSpp * sW[fi];
+            }
+            const uint32_t avail = slabEnd - slabCur;
+            const uint32_t rank = (uint32_t)__popc(need & ltMask);
+            if (!st.active && rank < avail)
+            {
+                int x = slabX0 + (int)(slabCur + rank), ri = slabRi0;
+                while (x >= p.width) { x -= p.width; ++ri; }
+                const int y = p.row0 + ri * p.rowStep;
+                st.rng = pixel_seed((uint32_t)(y * p.width + x) * (uint32_t)p.spp + slabSample, slabFrame);
+                float u = ((float)x + RandomFloat01(st.rng)) * p.invWidth;
+                float v = ((float)y + RandomFloat01(st.rng)) * p.invHeight;
+                Ray r = GetRay<false>(p.cam, u, v, st.rng);
+                st.o = r.orig; st.d = r.dir;
+                st.thr = v3(1, 1, 1); st.col = v3(0, 0, 0);
+                st.pixOff = (uint32_t)((p.packed ? ri : y) * p.width + x);
+                st.weight = slabW;
+                st.kind = 0; st.depth = 0; st.doMaterialE = true; st.active = true;
+            }
+            const uint32_t n = (uint32_t)__popc(need);
+            slabCur += n < avail ? n : avail;
+            need = __ballot_sync(0xffffffffu, !st.active);
+        }
+        if (!__any_sync(0xffffffffu, st.active)) break;
+
+        // ---- intersect
+        float t = TPT_MAX_T;
+        int id = -1;
+        if (st.active) { id = hitter.hit(sc, st.o, st.d, TPT_MIN_T, TPT_MAX_T, t); ++rc; }
+
+        // ---- shade
+        bool wantLight = false;
+        int lightFrom = 0;
+        bool finished = false;
+        if (st.active)
+        {
+            if (st.kind == 0)
+            {
+                if (id < 0) { st.col = st.col + st.thr * sky(st.d); finished = true; }
+                else
+                {
+                    Q4 s = ld_sph(sc, id);
+                    V3 pos = st.o + st.d * t;
+                    V3 normal = (pos - v3(s.x, s.y, s.z)) * sc.invRadius[id];
+                    const int mid = id < sc.count ? id : sc.count;
+                    Mat mat = load_mat(sc, mid);
+                    if (st.depth >= TPT_MAX_DEPTH) { st.col = st.col + st.thr * mat.emissive; finished = true; }
+                    else if (mat.type == kLambert)
+                    {
+                        if (st.doMaterialE) st.col = st.col + st.thr * mat.emissive;
+                        V3 target = normal + RandomUnitVector<false>(st.rng);
+                        st.nextDir = M<false>::normalize(target);
+                        st.thrAlb = st.thr * mat.albedo;
+                        st.albedo = mat.albedo;
+                        st.nl = dot(normal, st.d) < 0.0f ? normal : neg(normal);
+                        st.mid = mid;
+                        st.o = pos;
+                        wantLight = true; lightFrom = 0;
+                    }
+                    else if (mat.type == kMetal)
+                    {
+                        // Test.cpp:137-150; with roughness == 0 the unit-sphere sample has zero weight, so the fast
+                        // mode skips drawing it (the exact mode must draw it: it advances the shared RNG stream)
+                        V3 refl = reflect(st.d, normal);
+                        if (mat.roughness != 0.0f) refl = refl + mat.roughness * RandomInUnitSphere(st.rng);
+                        V3 outDir = M<false>::normalize(refl);
+                        if (dot(outDir, normal) > 0.0f)
+                        {
+                            if (st.doMaterialE) st.col = st.col + st.thr * mat.emissive;
+                            st.doMaterialE = true;
+                            st.thr = st.thr * mat.albedo;
+                            st.o = pos; st.d = outDir; ++st.depth;
+                        }
+                        else { st.col = st.col + st.thr * mat.emissive; finished = true; }
+                    }
+                    else
+                    {
+                        V3 att, outDir;
+                        bool ok = scatter_specular<false>(mat, st.d, pos, normal, st.rng, att, outDir);
+                        if (!ok) { st.col = st.col + st.thr * mat.emissive; finished = true; }
+                        else
+                        {
+                            if (st.doMaterialE) st.col = st.col + st.thr * mat.emissive;
+                            st.doMaterialE = true;
+                            st.thr = st.thr * att;
+                            st.o = pos; st.d = outDir; ++st.depth;
+                        }
+                    }
+                }
+            }
+            else
+            {
+                const int j = st.kind - 1;
+                if (id == sc.lights[j].id) st.col = st.col + st.pend;
+                wantLight = true; lightFrom = j + 1;
+            }
+        }
+        if (wantLight)
+        {
+            int j = lightFrom;
+            while (j < sc.nLights && sc.lights[j].id == st.mid) ++j;
+            if (j < sc.nLights)
+            {
+                const LightRec Lr = sc.lights[j];
+                V3 scn = v3(Lr.cx, Lr.cy, Lr.cz);
+                V3 pc = scn - st.o;
+                float d2 = dot(pc, pc);
+                float inv = rsqrtf(d2);
+                V3 sw = pc * inv;
+                V3 su = M<false>::normalize(cross(fabsf(sw.x) > 0.01f ? v3(0, 1, 0) : v3(1, 0, 0), sw));
+                V3 sv = cross(sw, su);
+                float cosAMax = M<false>::sqrt_(1.0f - Lr.radius * Lr.radius * inv * inv);
+                float eps1 = RandomFloat01(st.rng), eps2 = RandomFloat01(st.rng);
+                float cosA = 1.0f - eps1 + eps1 * cosAMax;
+                float sinA = M<false>::sqrt_(1.0f - cosA * cosA);
+                float phi = 2.0f * TPT_PI * eps2;
+                float sp, cp;
+                __sincosf(phi, &sp, &cp);
+                V3 l = su * (cp * sinA) + sv * (sp * sinA) + sw * cosA;
+                float omega = 2.0f * TPT_PI * (1.0f - cosAMax);
+                float dl = dot(l, st.nl);
+                float m = (0.0f < dl) ? dl : 0.0f;
+                st.pend = st.thr * ((st.albedo * v3(Lr.ex, Lr.ey, Lr.ez)) * (m * omega * (1.0f / TPT_PI)));
+                st.d = l;
+                st.kind = 1 + j;
+            }
+            else
+            {
+                st.d = st.nextDir;
+                st.thr = st.thrAlb;
+                st.kind = 0;
+                st.doMaterialE = false;
+                ++st.depth;
+            }
+        }
+        if (finished)
+        {
+            red_add_f4(p.image + (size_t)st.pixOff * 4, st.col.x * st.weight, st.col.y * st.weight, st.col.z * st.weight);
+            st.active = false;
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) rc += __shfl_xor_sync(0xffffffffu, rc, off);
+    if (lane == 0 && rc) atomicAdd(p.rayCounter, (unsigned long long)rc);
+}
+
+int fast_kernel_launches(const DrawParams&, int variant) { return variant >= 3 ? 2 : 1; }
+
 
 cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, int numSMs, cudaStream_t stream)
 {
@@ -342,6 +590,33 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
         e = cudaMemsetAsync(p.workCounter, 0, sizeof(unsigned int), stream);
         if (e != cudaSuccess) return e;
         kern<<<grid, kFastThreads, sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes, numTiles);
+        return cudaGetLastError();
+    }
+    if (variant == 3 || variant == 4)
+    {
+        auto kern = variant == 3 ? k_fast_queue<6> : k_fast_queue<8>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc.stagedBytes);
+        if (e != cudaSuccess) return e;
+        int perSM = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kQueueThreads, sc.stagedBytes);
+        if (e != cudaSuccess) return e;
+        if (perSM < 1) perSM = 1;
+        float wPrev = 1.0f;
+        for (int f = 0; f < p.numFrames; ++f) wPrev *= lerp_fac(p.frame0 + f, p.flags);
+        const long long regionPix = (long long)p.numRows * p.width;
+        k_prepare_image<<<(unsigned)((regionPix + 255) / 256), 256, 0, stream>>>(p, wPrev);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        const uint32_t S = (uint32_t)(p.spp * p.numFrames);
+        const long long slabs = ((regionPix + kSlabPix - 1) / kSlabPix) * S;
+        if (slabs > 0x7fffffffLL) return cudaErrorInvalidValue;
+        long long grid = (long long)numSMs * perSM;
+        const long long warpsNeeded = (slabs + 3) / 4;   // 4 warps per CTA
+        if (grid > warpsNeeded) grid = warpsNeeded;
+        e = cudaMemsetAsync(p.workCounter, 0, sizeof(unsigned int), stream);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)grid, kQueueThreads, sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes,
+                                                                      (uint32_t)slabs, S);
         return cudaGetLastError();
     }
     return cudaErrorInvalidValue;

@@ -209,11 +209,20 @@ TPT_HD Q4 ld_sph(const SceneView& sc, int i)
 }
 
 // Maths.cpp:97-102 / 171-176: the discriminant of one ray-sphere pair (shared by both passes below).
-TPT_HD float sphere_discr(const Q4 s, V3 o, V3 d, float& nb)
+template <bool EXACT> TPT_HD float sphere_discr(const Q4 s, V3 o, V3 d, float& nb)
 {
     float coX = s.x - o.x;
     float coY = s.y - o.y;
     float coZ = s.z - o.z;
+#if defined(__CUDA_ARCH__)
+    if (!EXACT)
+    {
+        // same polynomial, 10 instead of 11 FP32 issue slots: r^2 - |co|^2 folded into one FMA chain
+        nb = fmaf(coX, d.x, fmaf(coY, d.y, coZ * d.z));
+        float negc = fmaf(-coX, coX, fmaf(-coY, coY, fmaf(-coZ, coZ, s.w)));
+        return fmaf(nb, nb, negc);
+    }
+#endif
     nb = coX * d.x + coY * d.y + coZ * d.z;
     float c = coX * coX + coY * coY + coZ * coZ - s.w;
     return nb * nb - c;
@@ -235,7 +244,10 @@ template <bool EXACT> struct SerialHitter
         for (int base = 0; base < sc.simdCount; base += 32)
         {
             const int n = sc.simdCount - base < 32 ? sc.simdCount - base : 32;   // multiple of 4
-            uint32_t cand = 0;
+#if defined(__CUDA_ARCH__)
+            // sign bits of the discriminants, funnel-shifted into one word: after n spheres bit (n-1-k) holds
+            // sign(discr_k). Candidates = sign clear (discr > 0, +0 or NaN); pass 2 re-checks discr > 0.
+            uint32_t neg = 0;
 #pragma unroll
             for (int k = 0; k < 32; k += 4)
             {
@@ -245,26 +257,39 @@ template <bool EXACT> struct SerialHitter
                     for (int j = 0; j < 4; ++j)
                     {
                         float nb;
-                        float discr = sphere_discr(ld_sph(sc, base + k + j), o, d, nb);
-                        if (discr > 0.0f) cand |= 1u << (k + j);
+                        float discr = sphere_discr<EXACT>(ld_sph(sc, base + k + j), o, d, nb);
+                        neg = __funnelshift_l(__float_as_uint(discr), neg, 1);
                     }
                 }
             }
+            uint32_t cand = ~neg & (n == 32 ? 0xffffffffu : ((1u << n) - 1u));
             while (cand)
             {
-#if defined(__CUDA_ARCH__)
-                const int k = __ffs((int)cand) - 1;
+                const int bit = 31 - __clz((int)cand);     // highest bit first = lowest sphere index first
+                cand &= ~(1u << bit);
+                const int i = base + (n - 1 - bit);
 #else
+            uint32_t cand = 0;
+            for (int k = 0; k < n; ++k)
+            {
+                float nb;
+                if (sphere_discr<EXACT>(ld_sph(sc, base + k), o, d, nb) > 0.0f) cand |= 1u << k;
+            }
+            while (cand)
+            {
                 const int k = __builtin_ctz(cand);
-#endif
                 cand &= cand - 1;
                 const int i = base + k;
+#endif
                 float nb;
-                float discr = sphere_discr(ld_sph(sc, i), o, d, nb);
-                float discrSq = M<EXACT>::sqrt_(discr);
-                float t = nb - discrSq;
-                if (t <= tMin) t = nb + discrSq;
-                if (t > tMin && hit_better(t, i, bestT, bestId)) { bestT = t; bestId = i; }
+                float discr = sphere_discr<EXACT>(ld_sph(sc, i), o, d, nb);
+                if (discr > 0.0f)
+                {
+                    float discrSq = M<EXACT>::sqrt_(discr);
+                    float t = nb - discrSq;
+                    if (t <= tMin) t = nb + discrSq;
+                    if (t > tMin && hit_better(t, i, bestT, bestId)) { bestT = t; bestId = i; }
+                }
             }
         }
         tOut = bestT;
