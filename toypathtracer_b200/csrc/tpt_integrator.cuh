@@ -167,8 +167,9 @@ template <bool EXACT> TPT_HD Ray GetRay(const Camera88& c, float s, float t, uin
 // One sphere test, Maths.cpp:97-117 / 171-190. Candidate order is the SSE build's: smaller t wins; on an
 // exact tie the lower SIMD lane (id & 3) wins, then the lower id (Maths.cpp:113-117 keeps the first hit per
 // lane with a strict '<', Maths.cpp:126-152 picks the lowest lane among equal minima).
-TPT_HD bool hit_better(float t, int id, float bestT, int bestId)
+template <bool EXACT = true> TPT_HD bool hit_better(float t, int id, float bestT, int bestId)
 {
+    if (!EXACT) return t < bestT;          // ties have zero measure for independent random rays
     if (t < bestT) return true;
     if (t == bestT && bestId >= 0)
     {
@@ -209,7 +210,9 @@ TPT_HD Q4 ld_sph(const SceneView& sc, int i)
 }
 
 // Maths.cpp:97-102 / 171-176: the discriminant of one ray-sphere pair (shared by both passes below).
-template <bool EXACT> TPT_HD float sphere_discr(const Q4 s, V3 o, V3 d, float& nb)
+// `negc` receives r^2 - |co|^2 (fast form) or -(c) sign-equivalent information: negc < 0  <=>  c > 0 (ray origin
+// outside the sphere).
+template <bool EXACT> TPT_HD float sphere_discr(const Q4 s, V3 o, V3 d, float& nb, float& negc)
 {
     float coX = s.x - o.x;
     float coY = s.y - o.y;
@@ -219,13 +222,19 @@ template <bool EXACT> TPT_HD float sphere_discr(const Q4 s, V3 o, V3 d, float& n
     {
         // same polynomial, 10 instead of 11 FP32 issue slots: r^2 - |co|^2 folded into one FMA chain
         nb = fmaf(coX, d.x, fmaf(coY, d.y, coZ * d.z));
-        float negc = fmaf(-coX, coX, fmaf(-coY, coY, fmaf(-coZ, coZ, s.w)));
+        negc = fmaf(-coX, coX, fmaf(-coY, coY, fmaf(-coZ, coZ, s.w)));
         return fmaf(nb, nb, negc);
     }
 #endif
     nb = coX * d.x + coY * d.y + coZ * d.z;
     float c = coX * coX + coY * coY + coZ * coZ - s.w;
+    negc = -c;
     return nb * nb - c;
+}
+template <bool EXACT> TPT_HD float sphere_discr(const Q4 s, V3 o, V3 d, float& nb)
+{
+    float negc;
+    return sphere_discr<EXACT>(s, o, d, nb, negc);
 }
 
 // Every lane sweeps all spheres itself (lane = ray), in two passes per chunk of 32 spheres:
@@ -256,9 +265,14 @@ template <bool EXACT> struct SerialHitter
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                     {
-                        float nb;
-                        float discr = sphere_discr<EXACT>(ld_sph(sc, base + k + j), o, d, nb);
-                        neg = __funnelshift_l(__float_as_uint(discr), neg, 1);
+                        // Reject in pass 1 when discr < 0, or when the sphere lies wholly behind the origin:
+                        // nb < 0 (centre behind) and c > 0 (origin outside) => both roots <= 0 < tMin. With the
+                        // rounded values: discr <= fl(nb^2), so sqrt(discr) <= |nb| and nb + sqrt(discr) <= 0 —
+                        // the full test could never accept it, so skipping it changes nothing (exact mode too).
+                        float nb, negc;
+                        float discr = sphere_discr<EXACT>(ld_sph(sc, base + k + j), o, d, nb, negc);
+                        uint32_t rej = __float_as_uint(discr) | (__float_as_uint(nb) & __float_as_uint(negc));
+                        neg = __funnelshift_l(rej, neg, 1);
                     }
                 }
             }
@@ -288,7 +302,7 @@ template <bool EXACT> struct SerialHitter
                     float discrSq = M<EXACT>::sqrt_(discr);
                     float t = nb - discrSq;
                     if (t <= tMin) t = nb + discrSq;
-                    if (t > tMin && hit_better(t, i, bestT, bestId)) { bestT = t; bestId = i; }
+                    if (t > tMin && hit_better<EXACT>(t, i, bestT, bestId)) { bestT = t; bestId = i; }
                 }
             }
         }
