@@ -172,3 +172,22 @@ def test_4k_frame_ray_count(gpu_ctx, libs):
     buf = torch.zeros((2160, 3840, 4), dtype=torch.float32, device="cuda")
     rays = gpu_ctx.draw(0, 1, 3840, 2160, buf, flags=0, mode=0)
     assert [rays] == counts["3840x2160_flags0_frame0"]
+
+
+def test_headless_shell_same_output_as_reference_build(libs):
+    """One shell source (toypathtracer_b200/csrc/headless_main.cpp, the shape of Cpp/Emscripten/main.cpp:46-61) built
+    twice — against the unmodified reference sources (oracle/_ref/ref_headless) and against the drop-in
+    (toypathtracer_b200/tpt_headless) — must print the same ray counts and the same backbuffer checksum."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ours = os.path.join(root, "toypathtracer_b200", "tpt_headless")
+    ref = os.path.join(root, "oracle", "_ref", "ref_headless")
+    if not (os.path.exists(ours) and os.path.exists(ref)):
+        pytest.skip("headless binaries not built")
+    args = ["384", "216", "4", "2"]
+    env = dict(os.environ, TPT_MODE="exact")
+    a = subprocess.run([ours] + args, capture_output=True, text=True, env=env, timeout=300)
+    b = subprocess.run([ref] + args, capture_output=True, text=True, timeout=300)
+    assert a.returncode == 0, a.stderr
+    keep = lambda out: [l for l in out.splitlines() if l.startswith("frame") or l.startswith("checksum")]
+    assert keep(a.stdout) == keep(b.stdout) and len(keep(a.stdout)) == 5
