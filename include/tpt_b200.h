@@ -54,7 +54,9 @@ int tpt_set_spp(tpt_context* ctx, int spp);
 /* Implementation knobs (benchmarks/tests): "fast_variant" (0 megakernel, 1/2 persistent tiles, 3/4 persistent queue; default 3), "exact_lanes"
  * (0 auto, 1, 8, 32), "register_host" (1: page-lock the caller's host backbuffer with cudaHostRegister the first
  * time it is seen so both copies run at full PCIe rate; only safe when the buffer outlives the context, as a
- * reference shell's does; default 0 — buffers that are already pinned are detected by CUDA on their own). */
+ * reference shell's does; default 0 — buffers that are already pinned are detected by CUDA on their own), "host_bands" (1..8, default 3:
+ * host-buffer fast draws are split into row bands on separate streams so the D2H of one band overlaps the tracing of
+ * the next). */
 int tpt_set_option(tpt_context* ctx, const char* key, int value);
 
 /* Replaces DrawTest() (Test.cpp:344-367) for frames [frameCount, frameCount+numFrames) — numFrames*spp samples
@@ -86,6 +88,18 @@ int tpt_last_launch_count(tpt_context* ctx);
  * presentation step of the reference shells (Cpp/Windows/PixelShader.hlsl:1-15). dst = width*height*4 bytes. */
 int tpt_tonemap_srgb8(tpt_context* ctx, const float* image, int imageOnDevice, int width, int height,
                       unsigned char* dst, int dstOnDevice, void* cudaStream);
+
+/* Multi-GPU, one process per GPU: device memory that another process's kernels can write into directly over
+ * NVLink/NVSwitch (CUDA IPC). The root rank allocates the image and exports a 64-byte handle; every other rank
+ * opens it and passes the returned pointer as a device `backbuffer` to tpt_draw with its own row shard
+ * (row0 = rank, rowStep = world, packed = 0): the trace kernel's 128-bit stores / vector reductions then land in
+ * the root's HBM as the pixels finish — no separate gather. The reference has no counterpart (single device). */
+int tpt_mem_alloc(tpt_context* ctx, unsigned long long bytes, void** outDevPtr);      /* zero-filled */
+int tpt_mem_free(tpt_context* ctx, void* devPtr);
+int tpt_mem_copy(tpt_context* ctx, void* dst, const void* src, unsigned long long bytes, int kind /*1 H2D, 2 D2H, 3 D2D*/);
+int tpt_ipc_export(tpt_context* ctx, void* devPtr, void* outHandle64);
+int tpt_ipc_open(tpt_context* ctx, const void* handle64, void** outDevPtr);
+int tpt_ipc_close(tpt_context* ctx, void* devPtr);
 
 /* Diagnostic used by the parity tests: evaluates the device-side libm restatement the exact mode uses
  * (toypathtracer_b200/csrc/tpt_libm.cuh) on n host floats. fn: 0 = sinf, 1 = cosf, 2 = powf(x, 5). */

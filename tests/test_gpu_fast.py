@@ -97,3 +97,21 @@ def test_tonemap(gpu_ctx):
     ref = np.clip(np.maximum(1.055 * np.power(np.maximum(img[::-1, :, :3], 0), 0.416666667) - 0.055, 0), 0, 1) * 255 + 0.5
     assert np.abs(out[..., :3].astype(np.int32) - ref.astype(np.int32)).max() <= 1
     assert (out[..., 3] == 255).all()
+
+
+def test_host_band_pipelining_equals_single_launch(gpu_ctx):
+    """Host-buffer draws are split into row bands on separate streams (D2H of a band overlaps tracing of the next);
+    the image must equal the unsplit draw (same per-pixel streams; only the order of the L2 reductions differs)."""
+    sph, mats, cam, em = golden_scene()
+    gpu_ctx.set_scene(sph, mats, cam, em)
+    gpu_ctx.set_option("fast_variant", 3)
+    outs = []
+    for bands in (1, 4, 7):
+        gpu_ctx.set_option("host_bands", bands)
+        img = np.full((H, W, 4), 0.25, np.float32)
+        rays = gpu_ctx.draw(5, 2, W, H, img, flags=2, mode=1)
+        outs.append((img, rays))
+    gpu_ctx.set_option("host_bands", 4)
+    assert outs[0][1] == outs[1][1] == outs[2][1]
+    assert rel_l2(outs[1][0], outs[0][0]) < 1e-5 and rel_l2(outs[2][0], outs[0][0]) < 1e-5
+    assert (outs[1][0][..., 3] == np.float32(0.25)).all()      # progressive: alpha preserved

@@ -70,6 +70,13 @@ def _load_lib():
     L.tpt_last_launch_count.argtypes = [vp]; L.tpt_last_launch_count.restype = ci
     L.tpt_tonemap_srgb8.argtypes = [vp, vp, ci, ci, ci, vp, ci, vp]; L.tpt_tonemap_srgb8.restype = ci
     L.tpt_debug_libm.argtypes = [vp, ci, vp, vp, cll]; L.tpt_debug_libm.restype = ci
+    cull = ctypes.c_ulonglong
+    L.tpt_mem_alloc.argtypes = [vp, cull, ctypes.POINTER(vp)]; L.tpt_mem_alloc.restype = ci
+    L.tpt_mem_free.argtypes = [vp, vp]; L.tpt_mem_free.restype = ci
+    L.tpt_mem_copy.argtypes = [vp, vp, vp, cull, ci]; L.tpt_mem_copy.restype = ci
+    L.tpt_ipc_export.argtypes = [vp, vp, vp]; L.tpt_ipc_export.restype = ci
+    L.tpt_ipc_open.argtypes = [vp, vp, ctypes.POINTER(vp)]; L.tpt_ipc_open.restype = ci
+    L.tpt_ipc_close.argtypes = [vp, vp]; L.tpt_ipc_close.restype = ci
     _lib = L
     return L
 
@@ -78,8 +85,17 @@ def device_count() -> int:
     return int(_load_lib().tpt_device_count())
 
 
+class DevicePtr:
+    """A raw device address (e.g. an image living in another rank's HBM, opened with Context.ipc_open)."""
+
+    def __init__(self, addr: int):
+        self.addr = int(addr)
+
+
 def _as_ptr(buf) -> Tuple[int, bool, object]:
     """(address, on_device, keepalive) for a numpy array, a torch tensor or a raw device address."""
+    if isinstance(buf, DevicePtr):
+        return buf.addr, True, buf
     if isinstance(buf, np.ndarray):
         if buf.dtype != np.float32 or not buf.flags["C_CONTIGUOUS"]:
             raise TptError("backbuffer must be a C-contiguous float32 array")
@@ -178,6 +194,36 @@ class Context:
 
     def last_launch_count(self) -> int:
         return int(self._L.tpt_last_launch_count(self._h))
+
+    # ---- device memory shared between ranks (CUDA IPC), see include/tpt_b200.h
+    def mem_alloc(self, nbytes: int) -> DevicePtr:
+        p = ctypes.c_void_p()
+        self._check(self._L.tpt_mem_alloc(self._h, nbytes, ctypes.byref(p)), "tpt_mem_alloc")
+        return DevicePtr(p.value)
+
+    def mem_free(self, ptr: DevicePtr):
+        self._check(self._L.tpt_mem_free(self._h, ctypes.c_void_p(ptr.addr)), "tpt_mem_free")
+
+    def mem_to_host(self, ptr: DevicePtr, out: np.ndarray):
+        self._check(self._L.tpt_mem_copy(self._h, out.ctypes.data, ctypes.c_void_p(ptr.addr), out.nbytes, 2), "tpt_mem_copy")
+        return out
+
+    def mem_from_host(self, ptr: DevicePtr, src: np.ndarray):
+        src = np.ascontiguousarray(src)
+        self._check(self._L.tpt_mem_copy(self._h, ctypes.c_void_p(ptr.addr), src.ctypes.data, src.nbytes, 1), "tpt_mem_copy")
+
+    def ipc_export(self, ptr: DevicePtr) -> bytes:
+        h = ctypes.create_string_buffer(64)
+        self._check(self._L.tpt_ipc_export(self._h, ctypes.c_void_p(ptr.addr), h), "tpt_ipc_export")
+        return bytes(h.raw)
+
+    def ipc_open(self, handle: bytes) -> DevicePtr:
+        p = ctypes.c_void_p()
+        self._check(self._L.tpt_ipc_open(self._h, handle, ctypes.byref(p)), "tpt_ipc_open")
+        return DevicePtr(p.value)
+
+    def ipc_close(self, ptr: DevicePtr):
+        self._check(self._L.tpt_ipc_close(self._h, ctypes.c_void_p(ptr.addr)), "tpt_ipc_close")
 
     def debug_libm(self, fn: int, x: np.ndarray) -> np.ndarray:
         """Device-side libm restatement of the exact mode: fn 0 sinf, 1 cosf, 2 powf(x,5)."""

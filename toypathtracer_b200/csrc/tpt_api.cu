@@ -44,6 +44,13 @@ struct tpt_context
     unsigned long long* hPinned = nullptr; int hPinnedCap = 0;
     void* registeredPtr = nullptr; size_t registeredBytes = 0;
     int lastLaunches = 0;
+
+    // host-buffer draws: row bands pipelined over several streams (kernel of band b+1 overlaps D2H of band b)
+    static const int kMaxBands = 8;
+    int hostBands = 3;
+    cudaStream_t bandStream[kMaxBands] = {};
+    cudaEvent_t bandEvent[kMaxBands] = {};
+    cudaEvent_t forkEvent = nullptr;
 };
 
 static int fail(tpt_context* ctx, cudaError_t e, const char* what)
@@ -118,6 +125,15 @@ int tpt_create(int device, tpt_context** out)
     if (e == cudaSuccess) e = cudaMalloc(&ctx->dAccum, 2 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(ctx->dAccum, 0, 2 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->dWork, 64);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->forkEvent, cudaEventDisableTiming);
+    int prLo = 0, prHi = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prLo, &prHi);   // prHi is the numerically smallest
+    for (int b = 0; b < tpt_context::kMaxBands && e == cudaSuccess; ++b)
+    {
+        int pr = prHi + b; if (pr > prLo) pr = prLo;                              // earlier bands first
+        e = cudaStreamCreateWithPriority(&ctx->bandStream[b], cudaStreamNonBlocking, pr);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->bandEvent[b], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) { delete ctx; return (int)e; }
     *out = ctx;
     return 0;
@@ -132,6 +148,12 @@ void tpt_destroy(tpt_context* ctx)
     cudaFree(ctx->dBlob); cudaFree(ctx->dImage); cudaFree(ctx->dScratch); cudaFree(ctx->dRayCounters);
     cudaFree(ctx->dAccum); cudaFree(ctx->dWork);
     if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
+    for (int b = 0; b < tpt_context::kMaxBands; ++b)
+    {
+        if (ctx->bandStream[b]) cudaStreamDestroy(ctx->bandStream[b]);
+        if (ctx->bandEvent[b]) cudaEventDestroy(ctx->bandEvent[b]);
+    }
+    if (ctx->forkEvent) cudaEventDestroy(ctx->forkEvent);
     if (ctx->evStart) cudaEventDestroy(ctx->evStart);
     if (ctx->evStop) cudaEventDestroy(ctx->evStop);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -194,6 +216,7 @@ int tpt_set_option(tpt_context* ctx, const char* key, int value)
     if (!strcmp(key, "fast_variant")) { if (value < 0 || value > 4) return fail_msg(ctx, "fast_variant: 0..4"); ctx->fastVariant = value; return 0; }
     if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 8 && value != 32) return fail_msg(ctx, "exact_lanes: 0,1,8,32"); ctx->exactLanes = value; return 0; }
     if (!strcmp(key, "register_host")) { ctx->registerHost = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "host_bands")) { if (value < 1 || value > tpt_context::kMaxBands) return fail_msg(ctx, "host_bands: 1..8"); ctx->hostBands = value; return 0; }
     if (!strcmp(key, "max_scratch_mb")) { if (value < 16) return fail_msg(ctx, "max_scratch_mb: >= 16"); ctx->maxScratchBytes = (size_t)value << 20; return 0; }
     return fail_msg(ctx, "tpt_set_option: unknown key");
 }
@@ -289,7 +312,37 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
 
     ctx->lastLaunches = 0;
     CK(cudaEventRecord(ctx->evStart, stream), "event record");
-    for (int f = 0; f < numFrames; f += framesPerLaunch)
+    // Host-buffer fast draws: split the rows into bands, one stream per band (earlier band = higher priority). Each
+    // stream runs prepare + trace for its band and then copies the band to the caller's buffer, so the D2H of band b
+    // overlaps the tracing of band b+1 and the persistent CTAs of band b+1 fill the SMs as band b's tail drains.
+    bool pipelined = mode == TPT_MODE_FAST && !bufferOnDevice && ctx->fastVariant >= 3 && ctx->hostBands > 1 &&
+                     (rowStep == 1 || packed) && framesPerLaunch == numFrames && numRows >= 16 * ctx->hostBands;
+    if (pipelined)
+    {
+        const int NB = ctx->hostBands;
+        CK(cudaEventRecord(ctx->forkEvent, stream), "fork event");
+        p.frame0 = frameCount; p.numFrames = numFrames; p.rayCounter = ctx->dRayCounters;
+        for (int b = 0; b < NB; ++b)
+        {
+            const int rb0 = (int)((long long)numRows * b / NB), rb1 = (int)((long long)numRows * (b + 1) / NB);
+            cudaStream_t bs = ctx->bandStream[b];
+            CK(cudaStreamWaitEvent(bs, ctx->forkEvent, 0), "band wait");
+            DrawParams pb = p;
+            pb.row0 = row0 + rb0 * rowStep;
+            pb.numRows = rb1 - rb0;
+            pb.workCounter = ctx->dWork + b;
+            const size_t firstRow = packed ? (size_t)rb0 : (size_t)(row0 + rb0);   // rowStep == 1 when not packed
+            if (packed) pb.image = dImage + firstRow * width * 4;
+            cudaError_t e = launch_fast(pb, ctx->scene, ctx->fastVariant, ctx->numSMs, bs);
+            if (e != cudaSuccess) return fail(ctx, e, "kernel launch");
+            ctx->lastLaunches += fast_kernel_launches(pb, ctx->fastVariant);
+            const size_t off = firstRow * width * 4, bytes = (size_t)(rb1 - rb0) * width * 16;
+            CK(cudaMemcpyAsync(backbuffer + off, dImage + off, bytes, cudaMemcpyDeviceToHost, bs), "D2H band");
+            CK(cudaEventRecord(ctx->bandEvent[b], bs), "band event");
+            CK(cudaStreamWaitEvent(stream, ctx->bandEvent[b], 0), "join band");
+        }
+    }
+    for (int f = 0; f < numFrames && !pipelined; f += framesPerLaunch)
     {
         const int nf = numFrames - f < framesPerLaunch ? numFrames - f : framesPerLaunch;
         p.frame0 = frameCount + f;
@@ -321,7 +374,7 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
     k_accumulate_rays<<<1, 1, 0, stream>>>(ctx->dRayCounters, numFrames, ctx->dAccum);
     CK(cudaGetLastError(), "accumulate launch");
 
-    if (!bufferOnDevice)
+    if (!bufferOnDevice && !pipelined)
         CK(cudaMemcpyAsync(backbuffer, dImage, bufBytes, cudaMemcpyDeviceToHost, stream), "D2H backbuffer");
 
     if (outRayCount || outRaysPerFrame)
@@ -402,6 +455,56 @@ int tpt_tonemap_srgb8(tpt_context* ctx, const float* image, int imageOnDevice, i
         CK(cudaMemcpyAsync(dst, dOut, outBytes, cudaMemcpyDeviceToHost, stream), "D2H tonemap");
         CK(cudaStreamSynchronize(stream), "stream sync");
     }
+    return 0;
+}
+
+int tpt_mem_alloc(tpt_context* ctx, unsigned long long bytes, void** outDevPtr)
+{
+    if (!ctx || !outDevPtr || !bytes) return (int)cudaErrorInvalidValue;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CK(cudaMalloc(outDevPtr, (size_t)bytes), "cudaMalloc");
+    CK(cudaMemset(*outDevPtr, 0, (size_t)bytes), "cudaMemset");
+    return 0;
+}
+int tpt_mem_free(tpt_context* ctx, void* devPtr)
+{
+    if (!ctx) return (int)cudaErrorInvalidValue;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CK(cudaFree(devPtr), "cudaFree");
+    return 0;
+}
+int tpt_mem_copy(tpt_context* ctx, void* dst, const void* src, unsigned long long bytes, int kind)
+{
+    if (!ctx || !dst || !src || kind < 1 || kind > 3) return (int)cudaErrorInvalidValue;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CK(cudaStreamSynchronize(ctx->stream), "stream sync");
+    CK(cudaMemcpy(dst, src, (size_t)bytes, kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice), "cudaMemcpy");
+    return 0;
+}
+int tpt_ipc_export(tpt_context* ctx, void* devPtr, void* outHandle64)
+{
+    if (!ctx || !devPtr || !outHandle64) return (int)cudaErrorInvalidValue;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, devPtr), "cudaIpcGetMemHandle");
+    memcpy(outHandle64, &h, 64);
+    return 0;
+}
+int tpt_ipc_open(tpt_context* ctx, const void* handle64, void** outDevPtr)
+{
+    if (!ctx || !handle64 || !outDevPtr) return (int)cudaErrorInvalidValue;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CK(cudaIpcOpenMemHandle(outDevPtr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    return 0;
+}
+int tpt_ipc_close(tpt_context* ctx, void* devPtr)
+{
+    if (!ctx || !devPtr) return (int)cudaErrorInvalidValue;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CK(cudaIpcCloseMemHandle(devPtr), "cudaIpcCloseMemHandle");
     return 0;
 }
 
