@@ -11,9 +11,11 @@ os.makedirs(out_dir, exist_ok=True)
 ctx = tpt.Context(0)
 rows = []
 
-def run(name, scene, w, h, frame0, nframes, flags, mode, reps=3, expect_rays=None, spp=4, note=""):
+def run(name, scene, w, h, frame0, nframes, flags, mode, reps=3, expect_rays=None, spp=4, note="", variant=3):
     sph, mats, cam, em = scene
     ctx.set_scene(sph, mats, cam, em)
+    ctx.set_option("fast_variant", variant)
+    if mode == 1: note = (note + f" fast variant {variant}").strip()
     ctx.set_spp(spp)
     buf = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
     best = None
@@ -45,6 +47,9 @@ run("C2-correctness 1280x720 1024spp", ref720, 1280, 720, 0, 256, 2, 1, reps=1)
 run("C3 46 spheres 3840x2160 16spp", ref4k, 3840, 2160, 0, 4, 2, 1, reps=3)
 run("C3 46 spheres 3840x2160 16spp", ref4k, 3840, 2160, 0, 4, 2, 0, reps=1, expect_rays=605318173, note="golden SURVEY 9.9")
 run("C4 (1 GPU) 3840x2160 64spp", ref4k, 3840, 2160, 0, 16, 2, 1, reps=2, note="2.42 G rays: 64-bit counter")
+run("C4 (1 GPU) 3840x2160 64spp", ref4k, 3840, 2160, 0, 16, 2, 1, reps=2, variant=5)
+run("C3 46 spheres 3840x2160 16spp", ref4k, 3840, 2160, 0, 4, 2, 1, reps=3, variant=5)
+run("C2 46 spheres 1280x720 4spp", ref720, 1280, 720, 0, 1, 0, 1, reps=5, variant=5)
 run("C4 (1 GPU) 3840x2160 64spp", ref4k, 3840, 2160, 0, 16, 2, 0, reps=1, expect_rays=2421193362, note="golden SURVEY 9.9 (> INT_MAX)")
 stress = tpt.stress_scene(1920, 1080, 4096)
 run("C5 4096 spheres 1920x1080 8spp", stress, 1920, 1080, 0, 2, 2, 1, reps=2)
@@ -54,5 +59,5 @@ with open(os.path.join(out_dir, "configs.md"), "w") as f:
     f.write("| config | mode | rays | kernel ms | Mray/s | rays/sample | golden rays | sphere tests/s | alg. HBM GB/s |\n|---|---|---|---|---|---|---|---|---|\n")
     for r in rows:
         g = "" if "rays_expected" not in r else ("== %d" % r["rays_expected"] if r["rays_match"] else "MISMATCH %d" % r["rays_expected"])
-        f.write(f"| {r['config']} | {r['mode']} | {r['rays']} | {r['kernel_ms']:.2f} | {r['mray_s']:.0f} | {r['rays_per_sample']:.4f} | {g} | {r['sphere_tests_per_s']:.3e} | {r['hbm_gbs_algorithmic']:.1f} |\n")
+        f.write(f"| {r['config']} {r['note'] if r['mode']=='fast' else ''} | {r['mode']} | {r['rays']} | {r['kernel_ms']:.2f} | {r['mray_s']:.0f} | {r['rays_per_sample']:.4f} | {g} | {r['sphere_tests_per_s']:.3e} | {r['hbm_gbs_algorithmic']:.1f} |\n")
 print(open(os.path.join(out_dir, "configs.md")).read())

@@ -1,7 +1,7 @@
 """Strong scaling of ONE image across GPUs (BASELINE configs[3]: 3840x2160, 64 spp, rows interleaved over ranks).
 Run under torchrun. Two assembly methods:
   A  NCCL baseline: every rank renders a packed band (fast variant 3), one all_gather assembles the image;
-  B  fused peer write-out: every rank's tile kernel (fast variant 2) stores finished pixels straight into the
+  B  fused peer write-out: every rank's tile kernel (fast variant 5) stores finished pixels straight into the
      root's image over NVLink (CUDA IPC mapping), no gather — only a ray-count all_reduce as completion barrier.
 Prints one JSON line on rank 0."""
 import json, os, sys, time
@@ -47,7 +47,7 @@ ms_a, img_a = timed(method_a)
 rays_a = mg.sum_ray_counts(ctx.read_ray_count(sh), dev) // REPS
 
 # ---- B: fused peer write-out into the root's image
-ctx.set_option("fast_variant", 2)
+ctx.set_option("fast_variant", 5)
 shared = mg.SharedImage(ctx, W, H, rank)
 def method_b():
     ctx.draw(0, NF, W, H, shared.ptr, flags=2, mode=tpt.MODE_FAST, rows=(row0, nrows, step, 0), stream=sh, want_rays=False)
@@ -62,7 +62,7 @@ if rank == 0:
     rel = float(np.sqrt(((a - img_b) ** 2).sum() / (a ** 2).sum()))
     print(json.dumps({"workload": f"{W}x{H} {NF * 4} spp, 46 spheres, rows interleaved over {world} GPUs", "n_gpus": world,
                       "A_nccl_allgather": {"ms": ms_a, "mray_s": rays_a / ms_a / 1e3, "rays": rays_a, "kernel": "k_fast_queue (variant 3)"},
-                      "B_fused_peer_writeout": {"ms": ms_b, "mray_s": rays_b / ms_b / 1e3, "rays": rays_b, "kernel": "k_fast_persistent (variant 2)"},
+                      "B_fused_peer_writeout": {"ms": ms_b, "mray_s": rays_b / ms_b / 1e3, "rays": rays_b, "kernel": "k_fast_tileq (variant 5)"},
                       "relL2_A_vs_B": rel, "noise_floor_two_independent_renders": 0.194 / np.sqrt(NF * 4) * np.sqrt(2)}), flush=True)
 dist.barrier()
 shared.close()

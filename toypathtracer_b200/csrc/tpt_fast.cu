@@ -365,6 +365,124 @@ struct QPath
     bool active;
 };
 
+// One iteration of the per-lane path state machine shared by the queue kernels: intersect the lane's current ray
+// (path or shadow) against all spheres, then shade. Returns true when the lane's path has ended (st.col is final).
+__device__ __forceinline__ bool path_step(const SceneView& sc, QPath& st, unsigned& rc)
+{
+    SerialHitter<false> hitter;
+    // ---- intersect
+    float t = TPT_MAX_T;
+    int id = -1;
+    if (st.active) { id = hitter.hit(sc, st.o, st.d, TPT_MIN_T, TPT_MAX_T, t); ++rc; }
+
+    // ---- shade
+    bool wantLight = false;
+    int lightFrom = 0;
+    bool finished = false;
+    if (st.active)
+    {
+        if (st.kind == 0)
+        {
+            if (id < 0) { st.col = st.col + st.thr * sky(st.d); finished = true; }
+            else
+            {
+                Q4 s = ld_sph(sc, id);
+                V3 pos = st.o + st.d * t;
+                V3 normal = (pos - v3(s.x, s.y, s.z)) * sc.invRadius[id];
+                const int mid = id < sc.count ? id : sc.count;
+                Mat mat = load_mat(sc, mid);
+                if (st.depth >= TPT_MAX_DEPTH) { st.col = st.col + st.thr * mat.emissive; finished = true; }
+                else if (mat.type == kLambert)
+                {
+                    if (st.doMaterialE) st.col = st.col + st.thr * mat.emissive;
+                    V3 target = normal + RandomUnitVector<false>(st.rng);
+                    st.nextDir = M<false>::normalize(target);
+                    st.thrAlb = st.thr * mat.albedo;
+                    st.albedo = mat.albedo;
+                    st.nl = dot(normal, st.d) < 0.0f ? normal : neg(normal);
+                    st.mid = mid;
+                    st.o = pos;
+                    wantLight = true; lightFrom = 0;
+                }
+                else if (mat.type == kMetal)
+                {
+                    // Test.cpp:137-150; with roughness == 0 the unit-sphere sample has zero weight, so the fast
+                    // mode skips drawing it (the exact mode must draw it: it advances the shared RNG stream)
+                    V3 refl = reflect(st.d, normal);
+                    if (mat.roughness != 0.0f) refl = refl + mat.roughness * RandomInUnitSphere(st.rng);
+                    V3 outDir = M<false>::normalize(refl);
+                    if (dot(outDir, normal) > 0.0f)
+                    {
+                        if (st.doMaterialE) st.col = st.col + st.thr * mat.emissive;
+                        st.doMaterialE = true;
+                        st.thr = st.thr * mat.albedo;
+                        st.o = pos; st.d = outDir; ++st.depth;
+                    }
+                    else { st.col = st.col + st.thr * mat.emissive; finished = true; }
+                }
+                else
+                {
+                    V3 att, outDir;
+                    bool ok = scatter_specular<false>(mat, st.d, pos, normal, st.rng, att, outDir);
+                    if (!ok) { st.col = st.col + st.thr * mat.emissive; finished = true; }
+                    else
+                    {
+                        if (st.doMaterialE) st.col = st.col + st.thr * mat.emissive;
+                        st.doMaterialE = true;
+                        st.thr = st.thr * att;
+                        st.o = pos; st.d = outDir; ++st.depth;
+                    }
+                }
+            }
+        }
+        else
+        {
+            const int j = st.kind - 1;
+            if (id == sc.lights[j].id) st.col = st.col + st.pend;
+            wantLight = true; lightFrom = j + 1;
+        }
+    }
+    if (wantLight)
+    {
+        int j = lightFrom;
+        while (j < sc.nLights && sc.lights[j].id == st.mid) ++j;
+        if (j < sc.nLights)
+        {
+            const LightRec Lr = sc.lights[j];
+            V3 scn = v3(Lr.cx, Lr.cy, Lr.cz);
+            V3 pc = scn - st.o;
+            float d2 = dot(pc, pc);
+            float inv = rsqrtf(d2);
+            V3 sw = pc * inv;
+            V3 su = M<false>::normalize(cross(fabsf(sw.x) > 0.01f ? v3(0, 1, 0) : v3(1, 0, 0), sw));
+            V3 sv = cross(sw, su);
+            float cosAMax = M<false>::sqrt_(1.0f - Lr.radius * Lr.radius * inv * inv);
+            float eps1 = RandomFloat01(st.rng), eps2 = RandomFloat01(st.rng);
+            float cosA = 1.0f - eps1 + eps1 * cosAMax;
+            float sinA = M<false>::sqrt_(1.0f - cosA * cosA);
+            float phi = 2.0f * TPT_PI * eps2;
+            float sp, cp;
+            __sincosf(phi, &sp, &cp);
+            V3 l = su * (cp * sinA) + sv * (sp * sinA) + sw * cosA;
+            float omega = 2.0f * TPT_PI * (1.0f - cosAMax);
+            float dl = dot(l, st.nl);
+            float m = (0.0f < dl) ? dl : 0.0f;
+            st.pend = st.thr * ((st.albedo * v3(Lr.ex, Lr.ey, Lr.ez)) * (m * omega * (1.0f / TPT_PI)));
+            st.d = l;
+            st.kind = 1 + j;
+        }
+        else
+        {
+            st.d = st.nextDir;
+            st.thr = st.thrAlb;
+            st.kind = 0;
+            st.doMaterialE = false;
+            ++st.depth;
+        }
+    }
+    return finished;
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(kQueueThreads, MINB)
 k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights,
@@ -381,7 +499,7 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
     const unsigned ltMask = (1u << lane) - 1u;
     const uint32_t regionPix = (uint32_t)((long long)p.numRows * p.width);
     const float invSpp = 1.0f / (float)p.spp;
-    SerialHitter<false> hitter;
+    
     unsigned rc = 0;
 
     // warp-uniform slab cursor
@@ -439,116 +557,7 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
         }
         if (!__any_sync(0xffffffffu, st.active)) break;
 
-        // ---- intersect
-        float t = TPT_MAX_T;
-        int id = -1;
-        if (st.active) { id = hitter.hit(sc, st.o, st.d, TPT_MIN_T, TPT_MAX_T, t); ++rc; }
-
-        // ---- shade
-        bool wantLight = false;
-        int lightFrom = 0;
-        bool finished = false;
-        if (st.active)
-        {
-            if (st.kind == 0)
-            {
-                if (id < 0) { st.col = st.col + st.thr * sky(st.d); finished = true; }
-                else
-                {
-                    Q4 s = ld_sph(sc, id);
-                    V3 pos = st.o + st.d * t;
-                    V3 normal = (pos - v3(s.x, s.y, s.z)) * sc.invRadius[id];
-                    const int mid = id < sc.count ? id : sc.count;
-                    Mat mat = load_mat(sc, mid);
-                    if (st.depth >= TPT_MAX_DEPTH) { st.col = st.col + st.thr * mat.emissive; finished = true; }
-                    else if (mat.type == kLambert)
-                    {
-                        if (st.doMaterialE) st.col = st.col + st.thr * mat.emissive;
-                        V3 target = normal + RandomUnitVector<false>(st.rng);
-                        st.nextDir = M<false>::normalize(target);
-                        st.thrAlb = st.thr * mat.albedo;
-                        st.albedo = mat.albedo;
-                        st.nl = dot(normal, st.d) < 0.0f ? normal : neg(normal);
-                        st.mid = mid;
-                        st.o = pos;
-                        wantLight = true; lightFrom = 0;
-                    }
-                    else if (mat.type == kMetal)
-                    {
-                        // Test.cpp:137-150; with roughness == 0 the unit-sphere sample has zero weight, so the fast
-                        // mode skips drawing it (the exact mode must draw it: it advances the shared RNG stream)
-                        V3 refl = reflect(st.d, normal);
-                        if (mat.roughness != 0.0f) refl = refl + mat.roughness * RandomInUnitSphere(st.rng);
-                        V3 outDir = M<false>::normalize(refl);
-                        if (dot(outDir, normal) > 0.0f)
-                        {
-                            if (st.doMaterialE) st.col = st.col + st.thr * mat.emissive;
-                            st.doMaterialE = true;
-                            st.thr = st.thr * mat.albedo;
-                            st.o = pos; st.d = outDir; ++st.depth;
-                        }
-                        else { st.col = st.col + st.thr * mat.emissive; finished = true; }
-                    }
-                    else
-                    {
-                        V3 att, outDir;
-                        bool ok = scatter_specular<false>(mat, st.d, pos, normal, st.rng, att, outDir);
-                        if (!ok) { st.col = st.col + st.thr * mat.emissive; finished = true; }
-                        else
-                        {
-                            if (st.doMaterialE) st.col = st.col + st.thr * mat.emissive;
-                            st.doMaterialE = true;
-                            st.thr = st.thr * att;
-                            st.o = pos; st.d = outDir; ++st.depth;
-                        }
-                    }
-                }
-            }
-            else
-            {
-                const int j = st.kind - 1;
-                if (id == sc.lights[j].id) st.col = st.col + st.pend;
-                wantLight = true; lightFrom = j + 1;
-            }
-        }
-        if (wantLight)
-        {
-            int j = lightFrom;
-            while (j < sc.nLights && sc.lights[j].id == st.mid) ++j;
-            if (j < sc.nLights)
-            {
-                const LightRec Lr = sc.lights[j];
-                V3 scn = v3(Lr.cx, Lr.cy, Lr.cz);
-                V3 pc = scn - st.o;
-                float d2 = dot(pc, pc);
-                float inv = rsqrtf(d2);
-                V3 sw = pc * inv;
-                V3 su = M<false>::normalize(cross(fabsf(sw.x) > 0.01f ? v3(0, 1, 0) : v3(1, 0, 0), sw));
-                V3 sv = cross(sw, su);
-                float cosAMax = M<false>::sqrt_(1.0f - Lr.radius * Lr.radius * inv * inv);
-                float eps1 = RandomFloat01(st.rng), eps2 = RandomFloat01(st.rng);
-                float cosA = 1.0f - eps1 + eps1 * cosAMax;
-                float sinA = M<false>::sqrt_(1.0f - cosA * cosA);
-                float phi = 2.0f * TPT_PI * eps2;
-                float sp, cp;
-                __sincosf(phi, &sp, &cp);
-                V3 l = su * (cp * sinA) + sv * (sp * sinA) + sw * cosA;
-                float omega = 2.0f * TPT_PI * (1.0f - cosAMax);
-                float dl = dot(l, st.nl);
-                float m = (0.0f < dl) ? dl : 0.0f;
-                st.pend = st.thr * ((st.albedo * v3(Lr.ex, Lr.ey, Lr.ez)) * (m * omega * (1.0f / TPT_PI)));
-                st.d = l;
-                st.kind = 1 + j;
-            }
-            else
-            {
-                st.d = st.nextDir;
-                st.thr = st.thrAlb;
-                st.kind = 0;
-                st.doMaterialE = false;
-                ++st.depth;
-            }
-        }
+        const bool finished = path_step(sc, st, rc);
         if (finished)
         {
             red_add_f4(p.image + (size_t)st.pixOff * 4, st.col.x * st.weight, st.col.y * st.weight, st.col.z * st.weight);
@@ -559,7 +568,131 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
     if (lane == 0 && rc) atomicAdd(p.rayCounter, (unsigned long long)rc);
 }
 
-int fast_kernel_launches(const DrawParams&, int variant) { return variant >= 3 ? 2 : 1; }
+// ---- variant 5 ------------------------------------------------------------------------------------------------
+// "tile queue": the warp-level slab dealing and path state machine of variant 3, but a CTA owns a tile of kTileQPix
+// pixels for ALL its samples: radiance is accumulated in shared memory and the finished tile is written ONCE with
+// coalesced 128-bit stores (st.global.L1::no_allocate.v4, + 128-bit loads of `prev` when it has weight). The store
+// target may be another GPU's memory (CUDA IPC mapping): this is the fused render + gather of the multi-GPU path —
+// pixels leave over NVLink tile by tile while the other tiles are still being traced. One block barrier per tile; with
+// S = spp x frames >= 16 the per-tile tail is < 1 %, at S = 4 variant 3 is the better choice.
+constexpr int kTileQPix = 2048;
+
+template <int MINB>
+__global__ void __launch_bounds__(kQueueThreads, MINB)
+k_fast_tileq(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights,
+             uint32_t stagedBytes, uint32_t numTiles, uint32_t S, float wPrev)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ float sW[kMaxFramesPerDraw];
+    __shared__ float sAcc[kTileQPix * 3];
+    __shared__ uint32_t sTile, sSlab;
+    stage_blob(smem, blob, stagedBytes, &bar);
+    if (threadIdx.x == 0) { float wp; blend_weights(p, sW, wp); }
+    for (int i = threadIdx.x; i < kTileQPix * 3; i += kQueueThreads) sAcc[i] = 0.0f;
+    SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
+    const int lane = threadIdx.x & 31;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const uint32_t regionPix = (uint32_t)((long long)p.numRows * p.width);
+    const float invSpp = 1.0f / (float)p.spp;
+    unsigned rc = 0;
+
+    for (;;)
+    {
+        __syncthreads();
+        if (threadIdx.x == 0) { sTile = atomicAdd(p.workCounter, 1u); sSlab = 0; }
+        __syncthreads();
+        const uint32_t tile = sTile;
+        if (tile >= numTiles) break;
+        const uint32_t tilePix0 = tile * kTileQPix;
+        const uint32_t tilePix = regionPix - tilePix0 < (uint32_t)kTileQPix ? regionPix - tilePix0 : (uint32_t)kTileQPix;
+        const uint32_t slabsPerSample = (tilePix + kSlabPix - 1) / kSlabPix;
+        const uint32_t tileSlabs = slabsPerSample * S;
+
+        uint32_t slabCur = 0, slabEnd = 0, slabQ0 = 0;
+        int slabX0 = 0, slabRi0 = 0;
+        uint32_t slabSample = 0, slabFrame = 0;
+        float slabW = 0.0f;
+        bool exhausted = false;
+        QPath st;
+        st.active = false;
+        for (;;)
+        {
+            unsigned need = __ballot_sync(0xffffffffu, !st.active);
+            while (need && !exhausted)
+            {
+                if (slabCur >= slabEnd)
+                {
+                    uint32_t slab = 0;
+                    if (lane == 0) slab = atomicAdd(&sSlab, 1u);
+                    slab = __shfl_sync(0xffffffffu, slab, 0);
+                    if (slab >= tileSlabs) { exhausted = true; break; }
+                    const uint32_t s = slab / slabsPerSample, g = slab - s * slabsPerSample;   // sample-major inside the tile
+                    slabQ0 = g * kSlabPix;
+                    slabEnd = tilePix - slabQ0 < (uint32_t)kSlabPix ? tilePix - slabQ0 : (uint32_t)kSlabPix;
+                    slabCur = 0;
+                    const uint32_t pix0 = tilePix0 + slabQ0;
+                    slabRi0 = (int)(pix0 / (uint32_t)p.width);
+                    slabX0 = (int)(pix0 - (uint32_t)slabRi0 * (uint32_t)p.width);
+                    const uint32_t fi = s / (uint32_t)p.spp;
+                    slabSample = s - fi * (uint32_t)p.spp;
+                    slabFrame = (uint32_t)p.frame0 + fi;
+                    slabW = invSpp * sW[fi];
+                }
+                const uint32_t avail = slabEnd - slabCur;
+                const uint32_t rank = (uint32_t)__popc(need & ltMask);
+                if (!st.active && rank < avail)
+                {
+                    const uint32_t q = slabCur + rank;
+                    int x = slabX0 + (int)q, ri = slabRi0;
+                    while (x >= p.width) { x -= p.width; ++ri; }
+                    const int y = p.row0 + ri * p.rowStep;
+                    st.rng = pixel_seed((uint32_t)(y * p.width + x) * (uint32_t)p.spp + slabSample, slabFrame);
+                    float u = ((float)x + RandomFloat01(st.rng)) * p.invWidth;
+                    float v = ((float)y + RandomFloat01(st.rng)) * p.invHeight;
+                    Ray r = GetRay<false>(p.cam, u, v, st.rng);
+                    st.o = r.orig; st.d = r.dir;
+                    st.thr = v3(1, 1, 1); st.col = v3(0, 0, 0);
+                    st.pixOff = slabQ0 + q;                 // pixel index inside the tile
+                    st.weight = slabW;
+                    st.kind = 0; st.depth = 0; st.doMaterialE = true; st.active = true;
+                }
+                const uint32_t n = (uint32_t)__popc(need);
+                slabCur += n < avail ? n : avail;
+                need = __ballot_sync(0xffffffffu, !st.active);
+            }
+            if (!__any_sync(0xffffffffu, st.active)) break;
+            if (path_step(sc, st, rc))
+            {
+                atomicAdd(&sAcc[st.pixOff * 3 + 0], st.col.x * st.weight);
+                atomicAdd(&sAcc[st.pixOff * 3 + 1], st.col.y * st.weight);
+                atomicAdd(&sAcc[st.pixOff * 3 + 2], st.col.z * st.weight);
+                st.active = false;
+            }
+        }
+
+        // ---- tile finished: coalesced 128-bit write-out (possibly into a peer GPU's memory)
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < tilePix; i += kQueueThreads)
+        {
+            const uint32_t gp = tilePix0 + i;
+            const int ri = (int)(gp / (uint32_t)p.width), x = (int)(gp - (uint32_t)ri * (uint32_t)p.width);
+            const int y = p.row0 + ri * p.rowStep;
+            float* px = p.image + ((size_t)(p.packed ? ri : y) * p.width + x) * 4;
+            float4 prev = make_float4(0, 0, 0, 0);
+            if (wPrev != 0.0f) prev = ld_stream_f4(px);
+            prev.x = prev.x * wPrev + sAcc[i * 3 + 0];
+            prev.y = prev.y * wPrev + sAcc[i * 3 + 1];
+            prev.z = prev.z * wPrev + sAcc[i * 3 + 2];
+            st_stream_f4(px, prev);
+            sAcc[i * 3 + 0] = 0.0f; sAcc[i * 3 + 1] = 0.0f; sAcc[i * 3 + 2] = 0.0f;
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) rc += __shfl_xor_sync(0xffffffffu, rc, off);
+    if (lane == 0 && rc) atomicAdd(p.rayCounter, (unsigned long long)rc);
+}
+
+int fast_kernel_launches(const DrawParams&, int variant) { return (variant == 3 || variant == 4) ? 2 : 1; }
 
 
 cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, int numSMs, cudaStream_t stream)
@@ -617,6 +750,27 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
         if (e != cudaSuccess) return e;
         kern<<<(unsigned)grid, kQueueThreads, sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes,
                                                                       (uint32_t)slabs, S);
+        return cudaGetLastError();
+    }
+    if (variant == 5)
+    {
+        auto kern = k_fast_tileq<6>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc.stagedBytes);
+        if (e != cudaSuccess) return e;
+        int perSM = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kQueueThreads, sc.stagedBytes);
+        if (e != cudaSuccess) return e;
+        if (perSM < 1) perSM = 1;
+        float wPrev = 1.0f;
+        for (int f = 0; f < p.numFrames; ++f) wPrev *= lerp_fac(p.frame0 + f, p.flags);
+        const long long regionPix = (long long)p.numRows * p.width;
+        const long long tiles = (regionPix + kTileQPix - 1) / kTileQPix;
+        long long grid = (long long)numSMs * perSM;
+        if (grid > tiles) grid = tiles;
+        e = cudaMemsetAsync(p.workCounter, 0, sizeof(unsigned int), stream);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)grid, kQueueThreads, sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes,
+                                                                      (uint32_t)tiles, (uint32_t)(p.spp * p.numFrames), wPrev);
         return cudaGetLastError();
     }
     return cudaErrorInvalidValue;
