@@ -55,6 +55,14 @@ def method_b():
     return None
 ms_b, _ = timed(method_b)
 rays_b = mg.sum_ray_counts(ctx.read_ray_count(sh), dev) // REPS
+# diagnostics: the same tile kernel into LOCAL memory (packed band and strided full image), no collective
+local_full = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+ms_b_local_packed, _ = timed(lambda: ctx.draw(0, NF, W, H, band, flags=2, mode=tpt.MODE_FAST, rows=(row0, nrows, step, 1), stream=sh, want_rays=False))
+ms_b_local_strided, _ = timed(lambda: ctx.draw(0, NF, W, H, local_full, flags=2, mode=tpt.MODE_FAST, rows=(row0, nrows, step, 0), stream=sh, want_rays=False))
+ms_b_peer_nobarrier, _ = timed(lambda: ctx.draw(0, NF, W, H, shared.ptr, flags=2, mode=tpt.MODE_FAST, rows=(row0, nrows, step, 0), stream=sh, want_rays=False))
+ctx.set_option("fast_variant", 3)
+ms_a_kernel_only, _ = timed(lambda: ctx.draw(0, NF, W, H, band, flags=2, mode=tpt.MODE_FAST, rows=(row0, nrows, step, 1), stream=sh, want_rays=False))
+ctx.read_ray_count(sh)
 torch.cuda.synchronize(dev); dist.barrier()
 if rank == 0:
     img_b = shared.to_host()[..., :3].astype(np.float64)
@@ -63,7 +71,8 @@ if rank == 0:
     print(json.dumps({"workload": f"{W}x{H} {NF * 4} spp, 46 spheres, rows interleaved over {world} GPUs", "n_gpus": world,
                       "A_nccl_allgather": {"ms": ms_a, "mray_s": rays_a / ms_a / 1e3, "rays": rays_a, "kernel": "k_fast_queue (variant 3)"},
                       "B_fused_peer_writeout": {"ms": ms_b, "mray_s": rays_b / ms_b / 1e3, "rays": rays_b, "kernel": "k_fast_tileq (variant 5)"},
-                      "relL2_A_vs_B": rel, "noise_floor_two_independent_renders": 0.194 / np.sqrt(NF * 4) * np.sqrt(2)}), flush=True)
+                      "relL2_A_vs_B": rel, "diag_ms": {"v5_local_packed": ms_b_local_packed, "v5_local_strided": ms_b_local_strided,
+                                            "v5_peer_no_barrier": ms_b_peer_nobarrier, "v3_kernel_only": ms_a_kernel_only}, "noise_floor_two_independent_renders": 0.194 / np.sqrt(NF * 4) * np.sqrt(2)}), flush=True)
 dist.barrier()
 shared.close()
 dist.destroy_process_group()

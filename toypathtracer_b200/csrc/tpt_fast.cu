@@ -580,7 +580,7 @@ constexpr int kTileQPix = 2048;
 template <int MINB>
 __global__ void __launch_bounds__(kQueueThreads, MINB)
 k_fast_tileq(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights,
-             uint32_t stagedBytes, uint32_t numTiles, uint32_t S, float wPrev)
+             uint32_t stagedBytes, uint32_t numTiles, uint32_t S, float wPrev, uint32_t tileQPix)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
@@ -604,8 +604,8 @@ k_fast_tileq(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
         __syncthreads();
         const uint32_t tile = sTile;
         if (tile >= numTiles) break;
-        const uint32_t tilePix0 = tile * kTileQPix;
-        const uint32_t tilePix = regionPix - tilePix0 < (uint32_t)kTileQPix ? regionPix - tilePix0 : (uint32_t)kTileQPix;
+        const uint32_t tilePix0 = tile * tileQPix;
+        const uint32_t tilePix = regionPix - tilePix0 < tileQPix ? regionPix - tilePix0 : tileQPix;
         const uint32_t slabsPerSample = (tilePix + kSlabPix - 1) / kSlabPix;
         const uint32_t tileSlabs = slabsPerSample * S;
 
@@ -764,13 +764,20 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
         float wPrev = 1.0f;
         for (int f = 0; f < p.numFrames; ++f) wPrev *= lerp_fac(p.frame0 + f, p.flags);
         const long long regionPix = (long long)p.numRows * p.width;
-        const long long tiles = (regionPix + kTileQPix - 1) / kTileQPix;
+        // tile size: >= ~8192 paths per tile keeps the per-tile barrier tail < 1-2 %; then shrink (down to one slab)
+        // until there are >= 8 tiles per CTA so the end-of-kernel quantisation stays small on sharded images
+        const uint32_t S = (uint32_t)(p.spp * p.numFrames);
         long long grid = (long long)numSMs * perSM;
+        uint32_t tileQPix = (8192 / S + kSlabPix - 1) / kSlabPix * kSlabPix;
+        if (tileQPix < (uint32_t)kSlabPix) tileQPix = kSlabPix;
+        if (tileQPix > (uint32_t)kTileQPix) tileQPix = kTileQPix;
+        while (tileQPix > (uint32_t)kSlabPix && (regionPix + tileQPix - 1) / tileQPix < 8 * grid && tileQPix * S > 2048) tileQPix -= kSlabPix;
+        const long long tiles = (regionPix + tileQPix - 1) / tileQPix;
         if (grid > tiles) grid = tiles;
         e = cudaMemsetAsync(p.workCounter, 0, sizeof(unsigned int), stream);
         if (e != cudaSuccess) return e;
         kern<<<(unsigned)grid, kQueueThreads, sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes,
-                                                                      (uint32_t)tiles, (uint32_t)(p.spp * p.numFrames), wPrev);
+                                                                      (uint32_t)tiles, S, wPrev, tileQPix);
         return cudaGetLastError();
     }
     return cudaErrorInvalidValue;
