@@ -291,6 +291,23 @@ def main():
                                   "peak_def": "148 SM x 128 lanes x 1.965 GHz / 17 FP32 issue slots per test (no FMA)"}},
             "wall_s": wall,
         }
+        if world == 1 and args.mode == "fast":
+            # the bit-exact mode on the same step, for the record (same API, same buffers; latency-bound: one serial RNG
+            # chain per image row, Test.cpp:280)
+            ex_steps = 8
+            for s_ in range(2):
+                ctx.draw(s_, 1, W, H, image, flags=0, mode=tpt.MODE_EXACT, stream=sh, want_rays=False)
+            ctx.read_ray_count(sh)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            for s_ in range(ex_steps):
+                ctx.draw(2 + s_, 1, W, H, image, flags=0, mode=tpt.MODE_EXACT, stream=sh, want_rays=False)
+            ev1.record(stream)
+            torch.cuda.synchronize(dev)
+            ex_rays = ctx.read_ray_count(sh)
+            ex_ms = ev0.elapsed_time(ev1)
+            line["exact_mode"] = {"value": ex_rays / ex_ms / 1e3, "unit": "Mray/s", "ms_per_step": ex_ms / ex_steps, "steps": ex_steps,
+                                  "note": "TPT_MODE_EXACT: pixels and ray counts bit-identical to the reference CPU path"}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline_sample()
