@@ -213,7 +213,7 @@ int tpt_set_spp(tpt_context* ctx, int spp)
 int tpt_set_option(tpt_context* ctx, const char* key, int value)
 {
     if (!ctx || !key) return (int)cudaErrorInvalidValue;
-    if (!strcmp(key, "fast_variant")) { if (value < 0 || value > 5) return fail_msg(ctx, "fast_variant: 0..5"); ctx->fastVariant = value; return 0; }
+    if (!strcmp(key, "fast_variant")) { if (value < 0 || value > 7) return fail_msg(ctx, "fast_variant: 0..7"); ctx->fastVariant = value; return 0; }
     if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 8 && value != 32) return fail_msg(ctx, "exact_lanes: 0,1,8,32"); ctx->exactLanes = value; return 0; }
     if (!strcmp(key, "register_host")) { ctx->registerHost = value ? 1 : 0; return 0; }
     if (!strcmp(key, "host_bands")) { if (value < 1 || value > tpt_context::kMaxBands) return fail_msg(ctx, "host_bands: 1..8"); ctx->hostBands = value; return 0; }
@@ -315,7 +315,7 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
     // Host-buffer fast draws: split the rows into bands, one stream per band (earlier band = higher priority). Each
     // stream runs prepare + trace for its band and then copies the band to the caller's buffer, so the D2H of band b
     // overlaps the tracing of band b+1 and the persistent CTAs of band b+1 fill the SMs as band b's tail drains.
-    bool pipelined = mode == TPT_MODE_FAST && !bufferOnDevice && ctx->fastVariant >= 3 && ctx->fastVariant <= 5 && ctx->hostBands > 1 &&
+    bool pipelined = mode == TPT_MODE_FAST && !bufferOnDevice && ctx->fastVariant >= 3 && ctx->fastVariant <= 7 && ctx->hostBands > 1 &&
                      (rowStep == 1 || packed) && framesPerLaunch == numFrames && numRows >= 16 * ctx->hostBands;
     if (pipelined)
     {

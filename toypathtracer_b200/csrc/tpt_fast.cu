@@ -692,7 +692,333 @@ k_fast_tileq(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
     if (lane == 0 && rc) atomicAdd(p.rayCounter, (unsigned long long)rc);
 }
 
-int fast_kernel_launches(const DrawParams&, int variant) { return (variant == 3 || variant == 4) ? 2 : 1; }
+// ---- variant 6 ------------------------------------------------------------------------------------------------
+// "block wavefront": the persistent design of the north star taken literally. A CTA keeps kWaveSlots path slots in
+// SHARED memory (11 float4 per slot) and runs every iteration in three phases separated by block barriers:
+//   sweep     thread i regenerates slot i if it is free (next path of the CTA's chunk) and intersects slot i's
+//             ray (path or shadow) against all spheres -> every lane has a ray, no divergence outside pass 2;
+//   sort      the slot is classified {miss, lambert, metal, dielectric, shadow-return, terminal} and appended to
+//             that type's index list with warp __ballot_sync + prefix popcount (one shared atomic per warp per type);
+//   scatter   the lists are cut into 32-entry chunks and dealt to the warps: every warp shades entries of ONE
+//             material type (Scatter(), Test.cpp:83-193, without divergence); Lambert vertices and returning
+//             shadow rays append themselves to the light list, processed the same way in a third phase
+//             (explicit light sampling, Test.cpp:96-133).
+// Radiance leaves through the same 128-bit vector reductions as variant 3.
+constexpr int kWaveThreads = 256;
+constexpr int kWaveSlots = 256;        // one slot per thread
+constexpr int kWaveFields = 11;
+constexpr int kWaveChunk = 4096;       // paths taken from the global counter at a time
+enum { WF_O = 0, WF_D, WF_THR, WF_COL, WF_NEXT, WF_THRALB, WF_NL, WF_ALB, WF_PEND, WF_POS, WF_NRM };
+enum { WT_MISS = 0, WT_LAMBERT, WT_METAL, WT_DIEL, WT_SHADOW, WT_TERMINAL, WT_COUNT };
+constexpr int kKindFree = 255;
+
+struct FastDiv { uint32_t mul, shift, d; };   // n / d for n < 2^31
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv f) { return f.d == 1 ? n : (uint32_t)__umulhi(n, f.mul) >> f.shift; }
+static FastDiv make_fastdiv(uint32_t d)
+{
+    FastDiv f; f.d = d; f.mul = 0; f.shift = 0;
+    if (d <= 1) return f;
+    uint32_t l = 0; while ((1u << l) < d) ++l;                    // ceil(log2 d)
+    const uint64_t m = ((1ull << (32 + l)) + d - 1) / d;            // may need 33 bits
+    if (m >> 32) { const uint64_t m2 = ((1ull << (31 + l)) + d - 1) / d; f.mul = (uint32_t)m2; f.shift = l - 1; }  // exact for n < 2^31
+    else { f.mul = (uint32_t)m; f.shift = l; }
+    return f;
+}
+
+struct WaveArgs
+{
+    uint32_t totalPaths, S;
+    FastDiv divS, divW, divSpp;
+};
+
+template <int MINB>
+__global__ void __launch_bounds__(kWaveThreads, MINB)
+k_fast_wave(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights,
+            uint32_t stagedBytes, uint32_t poolOffset, WaveArgs wa)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ float sW[kMaxFramesPerDraw];
+    __shared__ uint16_t sList[WT_COUNT][kWaveSlots];
+    __shared__ uint16_t sLight[kWaveSlots];
+    __shared__ int sCount[WT_COUNT];
+    __shared__ int sLightCount;
+    __shared__ uint32_t sNextPath, sEndPath;
+    __shared__ int sExhausted, sLive;
+    stage_blob(smem, blob, stagedBytes, &bar);
+    float4* pool = reinterpret_cast<float4*>(smem + poolOffset);
+#define WFLD(f, slot) pool[(f) * kWaveSlots + (slot)]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned ltMask = (1u << lane) - 1u;
+    if (tid == 0)
+    {
+        float wp; blend_weights(p, sW, wp);
+        sNextPath = 0; sEndPath = 0; sExhausted = 0; sLive = 0; sLightCount = 0;
+        for (int t = 0; t < WT_COUNT; ++t) sCount[t] = 0;
+    }
+    WFLD(WF_D, tid) = make_float4(0, 0, 0, __int_as_float(kKindFree));
+    SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
+    const float invSpp = 1.0f / (float)p.spp;
+    SerialHitter<false> hitter;
+    unsigned rc = 0;
+    __syncthreads();
+
+    for (;;)
+    {
+        // ---- chunk refill (one thread), visible after the barrier
+        if (tid == 0 && !sExhausted && sNextPath >= sEndPath)
+        {
+            const uint32_t base = atomicAdd(p.workCounter, (unsigned)kWaveChunk);
+            if (base >= wa.totalPaths) sExhausted = 1;
+            else { sNextPath = base; sEndPath = base + kWaveChunk < wa.totalPaths ? base + kWaveChunk : wa.totalPaths; }
+        }
+        __syncthreads();
+
+        // ---- phase 1: regenerate own slot if free, then sweep
+        float4 fd = WFLD(WF_D, tid);
+        int misc = __float_as_int(fd.w);
+        int kind = misc & 0xff;
+        {
+            const unsigned need = __ballot_sync(0xffffffffu, kind == kKindFree);
+            if (need)
+            {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&sNextPath, (uint32_t)__popc(need));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const uint32_t idx = base + (uint32_t)__popc(need & ltMask);
+                if (kind == kKindFree && idx < sEndPath)
+                {
+                    const uint32_t slab = idx >> 7, q = idx & 127u;
+                    const uint32_t mtile = fdiv(slab, wa.divS), s = slab - mtile * wa.S;
+                    uint32_t pix = mtile * 128u + q;
+                    const uint32_t regionPix = (uint32_t)p.numRows * (uint32_t)p.width;
+                    if (pix < regionPix)
+                    {
+                        const uint32_t ri = fdiv(pix, wa.divW), x = pix - ri * (uint32_t)p.width;
+                        const uint32_t fi = fdiv(s, wa.divSpp), ss = s - fi * (uint32_t)p.spp;
+                        const int y = p.row0 + (int)ri * p.rowStep;
+                        uint32_t rng = pixel_seed((uint32_t)(y * p.width + (int)x) * (uint32_t)p.spp + ss, (uint32_t)p.frame0 + fi);
+                        float u = ((float)x + RandomFloat01(rng)) * p.invWidth;
+                        float v = ((float)y + RandomFloat01(rng)) * p.invHeight;
+                        Ray r = GetRay<false>(p.cam, u, v, rng);
+                        kind = 0; misc = 0 | (0 << 8) | (1 << 16);
+                        fd = make_float4(r.dir.x, r.dir.y, r.dir.z, __int_as_float(misc));
+                        WFLD(WF_O, tid) = make_float4(r.orig.x, r.orig.y, r.orig.z, 0.0f);
+                        WFLD(WF_D, tid) = fd;
+                        WFLD(WF_THR, tid) = make_float4(1, 1, 1, __uint_as_float(rng));
+                        WFLD(WF_COL, tid) = make_float4(0, 0, 0, __uint_as_float((uint32_t)((p.packed ? (int)ri : y) * p.width + (int)x)));
+                        WFLD(WF_NEXT, tid) = make_float4(0, 0, 0, invSpp * sW[fi]);
+                    }
+                }
+            }
+        }
+        int type = -1;
+        if (kind != kKindFree)
+        {
+            const float4 fo = WFLD(WF_O, tid);
+            const V3 o = v3(fo.x, fo.y, fo.z), d = v3(fd.x, fd.y, fd.z);
+            float t;
+            const int id = hitter.hit(sc, o, d, TPT_MIN_T, TPT_MAX_T, t);
+            ++rc;
+            if (kind != 0) { type = WT_SHADOW; WFLD(WF_POS, tid).w = __int_as_float(id); }
+            else if (id < 0) type = WT_MISS;
+            else
+            {
+                const Q4 s = ld_sph(sc, id);
+                const V3 pos = o + d * t;
+                const V3 normal = (pos - v3(s.x, s.y, s.z)) * sc.invRadius[id];
+                const int mid = id < sc.count ? id : sc.count;
+                const int depth = (misc >> 8) & 0xff;
+                const int mtype = f_as_i(sc.matA[mid].w);
+                type = depth >= TPT_MAX_DEPTH ? WT_TERMINAL : (mtype == kLambert ? WT_LAMBERT : (mtype == kMetal ? WT_METAL : WT_DIEL));
+                WFLD(WF_POS, tid) = make_float4(pos.x, pos.y, pos.z, __int_as_float(mid));
+                WFLD(WF_NRM, tid) = make_float4(normal.x, normal.y, normal.z, 0.0f);
+            }
+        }
+        // ---- phase 2: sort slots by type (ballot + prefix)
+#pragma unroll
+        for (int T = 0; T < WT_COUNT; ++T)
+        {
+            const unsigned m = __ballot_sync(0xffffffffu, type == T);
+            if (m)
+            {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&sCount[T], __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (type == T) sList[T][base + __popc(m & ltMask)] = (uint16_t)tid;
+            }
+        }
+        __syncthreads();
+        const int live = sCount[0] + sCount[1] + sCount[2] + sCount[3] + sCount[4] + sCount[5];
+        if (live == 0 && sExhausted) break;
+
+        // ---- phase 3: Scatter() per material type, 32-entry chunks dealt to the warps
+        {
+            int chunk = warp;               // chunk ids over the concatenation of the type lists
+            int T = 0, first = 0;           // `first` = chunk id of type T's first chunk
+            for (;;)
+            {
+                while (T < WT_COUNT && chunk >= first + ((sCount[T] + 31) >> 5)) { first += (sCount[T] + 31) >> 5; ++T; }
+                if (T >= WT_COUNT) break;
+                const int k = ((chunk - first) << 5) + lane;
+                const bool on = k < sCount[T];
+                const int slot = on ? sList[T][k] : 0;
+                bool wantLight = false, finished = false;
+                float4 fcol, fthr;
+                if (on)
+                {
+                    fcol = WFLD(WF_COL, slot);
+                    fthr = WFLD(WF_THR, slot);
+                    float4 fdd = WFLD(WF_D, slot);
+                    int m2 = __float_as_int(fdd.w);
+                    V3 col = v3(fcol.x, fcol.y, fcol.z), thr = v3(fthr.x, fthr.y, fthr.z);
+                    uint32_t rng = __float_as_uint(fthr.w);
+                    const V3 d = v3(fdd.x, fdd.y, fdd.z);
+                    const bool doMatE = (m2 >> 16) & 1;
+                    if (T == WT_MISS) { col = col + thr * sky(d); finished = true; }
+                    else if (T == WT_SHADOW)
+                    {
+                        const int j = (m2 & 0xff) - 1;
+                        const int hid = __float_as_int(WFLD(WF_POS, slot).w);
+                        if (hid == sc.lights[j].id) { const float4 pe = WFLD(WF_PEND, slot); col = col + v3(pe.x, pe.y, pe.z); }
+                        wantLight = true;   // next light index = j + 1, kept in kind
+                    }
+                    else
+                    {
+                        const float4 fp = WFLD(WF_POS, slot), fn = WFLD(WF_NRM, slot);
+                        const V3 pos = v3(fp.x, fp.y, fp.z), normal = v3(fn.x, fn.y, fn.z);
+                        const int mid = __float_as_int(fp.w);
+                        const Mat mat = load_mat(sc, mid);
+                        if (T == WT_TERMINAL) { col = col + thr * mat.emissive; finished = true; }
+                        else if (T == WT_LAMBERT)
+                        {
+                            if (doMatE) col = col + thr * mat.emissive;
+                            const V3 target = normal + RandomUnitVector<false>(rng);
+                            const V3 nextDir = M<false>::normalize(target);
+                            const V3 nl = dot(normal, d) < 0.0f ? normal : neg(normal);
+                            const V3 thrAlb = thr * mat.albedo;
+                            WFLD(WF_NEXT, slot) = make_float4(nextDir.x, nextDir.y, nextDir.z, WFLD(WF_NEXT, slot).w);
+                            WFLD(WF_THRALB, slot) = make_float4(thrAlb.x, thrAlb.y, thrAlb.z, __int_as_float(mid));
+                            WFLD(WF_NL, slot) = make_float4(nl.x, nl.y, nl.z, 0.0f);
+                            WFLD(WF_ALB, slot) = make_float4(mat.albedo.x, mat.albedo.y, mat.albedo.z, 0.0f);
+                            WFLD(WF_O, slot) = make_float4(pos.x, pos.y, pos.z, 0.0f);
+                            m2 = (m2 & ~0xff) | 0;      // kind := "before light 0" (light phase advances it)
+                            wantLight = true;
+                        }
+                        else
+                        {
+                            V3 att, outDir;
+                            bool ok;
+                            if (T == WT_METAL)
+                            {
+                                V3 refl = reflect(d, normal);
+                                if (mat.roughness != 0.0f) refl = refl + mat.roughness * RandomInUnitSphere(rng);
+                                outDir = M<false>::normalize(refl);
+                                att = mat.albedo;
+                                ok = dot(outDir, normal) > 0.0f;
+                            }
+                            else ok = scatter_specular<false>(mat, d, pos, normal, rng, att, outDir);
+                            if (!ok) { col = col + thr * mat.emissive; finished = true; }
+                            else
+                            {
+                                if (doMatE) col = col + thr * mat.emissive;
+                                thr = thr * att;
+                                const int depth = ((m2 >> 8) & 0xff) + 1;
+                                m2 = 0 | (depth << 8) | (1 << 16);
+                                WFLD(WF_O, slot) = make_float4(pos.x, pos.y, pos.z, 0.0f);
+                                fdd = make_float4(outDir.x, outDir.y, outDir.z, 0.0f);
+                            }
+                        }
+                    }
+                    if (finished)
+                    {
+                        const float w = WFLD(WF_NEXT, slot).w;
+                        red_add_f4(p.image + (size_t)__float_as_uint(fcol.w) * 4, col.x * w, col.y * w, col.z * w);
+                        m2 = kKindFree;
+                    }
+                    fdd.w = __int_as_float(m2);
+                    WFLD(WF_D, slot) = fdd;
+                    WFLD(WF_COL, slot) = make_float4(col.x, col.y, col.z, fcol.w);
+                    WFLD(WF_THR, slot) = make_float4(thr.x, thr.y, thr.z, __uint_as_float(rng));
+                }
+                const unsigned lm = __ballot_sync(0xffffffffu, wantLight);
+                if (lm)
+                {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&sLightCount, __popc(lm));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (wantLight) sLight[base + __popc(lm & ltMask)] = (uint16_t)slot;
+                }
+                chunk += kWaveThreads / 32;
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 4: explicit light sampling for Lambert vertices / returning shadow rays (Test.cpp:96-133)
+        {
+            const int nL = sLightCount;
+            for (int k = tid; k < ((nL + 31) & ~31); k += kWaveThreads)
+            {
+                if (k < nL)
+                {
+                    const int slot = sLight[k];
+                    float4 fdd = WFLD(WF_D, slot);
+                    int m2 = __float_as_int(fdd.w);
+                    const float4 fta = WFLD(WF_THRALB, slot);
+                    const int mid = __float_as_int(fta.w);
+                    int j = m2 & 0xff;                 // kind k = shadow ray of light k-1 just returned -> next is light k
+                    while (j < sc.nLights && sc.lights[j].id == mid) ++j;
+                    if (j < sc.nLights)
+                    {
+                        const LightRec Lr = sc.lights[j];
+                        const float4 fo = WFLD(WF_O, slot), fnl = WFLD(WF_NL, slot), fal = WFLD(WF_ALB, slot);
+                        float4 fthr = WFLD(WF_THR, slot);
+                        uint32_t rng = __float_as_uint(fthr.w);
+                        const V3 o = v3(fo.x, fo.y, fo.z);
+                        V3 pc = v3(Lr.cx, Lr.cy, Lr.cz) - o;
+                        float d2 = dot(pc, pc);
+                        float inv = rsqrtf(d2);
+                        V3 sw = pc * inv;
+                        V3 su = M<false>::normalize(cross(fabsf(sw.x) > 0.01f ? v3(0, 1, 0) : v3(1, 0, 0), sw));
+                        V3 sv = cross(sw, su);
+                        float cosAMax = M<false>::sqrt_(1.0f - Lr.radius * Lr.radius * inv * inv);
+                        float eps1 = RandomFloat01(rng), eps2 = RandomFloat01(rng);
+                        float cosA = 1.0f - eps1 + eps1 * cosAMax;
+                        float sinA = M<false>::sqrt_(1.0f - cosA * cosA);
+                        float sp, cp;
+                        __sincosf(2.0f * TPT_PI * eps2, &sp, &cp);
+                        V3 l = su * (cp * sinA) + sv * (sp * sinA) + sw * cosA;
+                        float omega = 2.0f * TPT_PI * (1.0f - cosAMax);
+                        float dl = dot(l, v3(fnl.x, fnl.y, fnl.z));
+                        float m = (0.0f < dl) ? dl : 0.0f;
+                        V3 pend = v3(fthr.x, fthr.y, fthr.z) * ((v3(fal.x, fal.y, fal.z) * v3(Lr.ex, Lr.ey, Lr.ez)) * (m * omega * (1.0f / TPT_PI)));
+                        WFLD(WF_PEND, slot) = make_float4(pend.x, pend.y, pend.z, 0.0f);
+                        fthr.w = __uint_as_float(rng);
+                        WFLD(WF_THR, slot) = fthr;
+                        m2 = (m2 & ~0xff) | (1 + j);
+                        WFLD(WF_D, slot) = make_float4(l.x, l.y, l.z, __int_as_float(m2));
+                    }
+                    else
+                    {
+                        const float4 fnx = WFLD(WF_NEXT, slot);
+                        float4 fthr = WFLD(WF_THR, slot);
+                        const int depth = ((m2 >> 8) & 0xff) + 1;
+                        m2 = 0 | (depth << 8) | (0 << 16);       // doMaterialE = false after a Lambert vertex (Test.cpp:214)
+                        WFLD(WF_D, slot) = make_float4(fnx.x, fnx.y, fnx.z, __int_as_float(m2));
+                        WFLD(WF_THR, slot) = make_float4(fta.x, fta.y, fta.z, fthr.w);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { sLightCount = 0; for (int t = 0; t < WT_COUNT; ++t) sCount[t] = 0; }
+    }
+#undef WFLD
+    for (int off = 16; off > 0; off >>= 1) rc += __shfl_xor_sync(0xffffffffu, rc, off);
+    if (lane == 0 && rc) atomicAdd(p.rayCounter, (unsigned long long)rc);
+}
+
+int fast_kernel_launches(const DrawParams&, int variant) { return (variant == 3 || variant == 4 || variant == 6 || variant == 7) ? 2 : 1; }
 
 
 cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, int numSMs, cudaStream_t stream)
@@ -750,6 +1076,37 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
         if (e != cudaSuccess) return e;
         kern<<<(unsigned)grid, kQueueThreads, sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes,
                                                                       (uint32_t)slabs, S);
+        return cudaGetLastError();
+    }
+    if (variant == 6 || variant == 7)
+    {
+        auto kern = variant == 6 ? k_fast_wave<3> : k_fast_wave<4>;
+        const uint32_t poolOffset = (sc.stagedBytes + 127u) & ~127u;
+        const size_t dyn = (size_t)poolOffset + (size_t)kWaveFields * kWaveSlots * 16;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return e;
+        int perSM = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kWaveThreads, dyn);
+        if (e != cudaSuccess) return e;
+        if (perSM < 1) perSM = 1;
+        float wPrev = 1.0f;
+        for (int f = 0; f < p.numFrames; ++f) wPrev *= lerp_fac(p.frame0 + f, p.flags);
+        const long long regionPix = (long long)p.numRows * p.width;
+        k_prepare_image<<<(unsigned)((regionPix + 255) / 256), 256, 0, stream>>>(p, wPrev);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        WaveArgs wa;
+        wa.S = (uint32_t)(p.spp * p.numFrames);
+        const long long total = ((regionPix + 127) / 128) * 128 * wa.S;      // whole 128-pixel slabs; tail pixels are skipped
+        if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
+        wa.totalPaths = (uint32_t)total;
+        wa.divS = make_fastdiv(wa.S); wa.divW = make_fastdiv((uint32_t)p.width); wa.divSpp = make_fastdiv((uint32_t)p.spp);
+        long long grid = (long long)numSMs * perSM;
+        const long long need = (total + kWaveChunk - 1) / kWaveChunk;
+        if (grid > need) grid = need;
+        e = cudaMemsetAsync(p.workCounter, 0, sizeof(unsigned int), stream);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)grid, kWaveThreads, dyn, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes, poolOffset, wa);
         return cudaGetLastError();
     }
     if (variant == 5)
