@@ -589,7 +589,7 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
 // target may be another GPU's memory (CUDA IPC mapping): this is the fused render + gather of the multi-GPU path —
 // pixels leave over NVLink tile by tile while the other tiles are still being traced. One block barrier per tile; with
 // S = spp x frames >= 16 the per-tile tail is < 1 %, at S = 4 variant 3 is the better choice.
-constexpr int kTileQPix = 2048;
+constexpr int kTileQPix = 1024;
 
 template <int MINB>
 __global__ void __launch_bounds__(kQueueThreads, MINB)
@@ -600,6 +600,7 @@ k_fast_tileq(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
     __shared__ uint64_t bar;
     __shared__ float sW[kMaxFramesPerDraw];
     __shared__ float sAcc[kTileQPix * 3];
+    __shared__ float4 sRays[kQueueThreads / 32][kSlabPix][2];   // see k_fast_queue
     __shared__ uint32_t sTile, sSlab;
     stage_blob(smem, blob, stagedBytes, &bar);
     if (threadIdx.x == 0) { float wp; blend_weights(p, sW, wp); }
@@ -652,22 +653,31 @@ k_fast_tileq(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
                     slabSample = s - fi * (uint32_t)p.spp;
                     slabFrame = (uint32_t)p.frame0 + fi;
                     slabW = invSpp * sW[fi];
+                    __syncwarp();
+                    for (uint32_t q = (uint32_t)lane; q < slabEnd; q += 32)
+                    {
+                        int x = slabX0 + (int)q, ri = slabRi0;
+                        while (x >= p.width) { x -= p.width; ++ri; }
+                        const int y = p.row0 + ri * p.rowStep;
+                        uint32_t rng = pixel_seed((uint32_t)(y * p.width + x) * (uint32_t)p.spp + slabSample, slabFrame);
+                        float u = ((float)x + RandomFloat01(rng)) * p.invWidth;
+                        float v = ((float)y + RandomFloat01(rng)) * p.invHeight;
+                        Ray r = GetRay<false>(p.cam, u, v, rng);
+                        sRays[threadIdx.x >> 5][q][0] = make_float4(r.orig.x, r.orig.y, r.orig.z, __uint_as_float(rng));
+                        sRays[threadIdx.x >> 5][q][1] = make_float4(r.dir.x, r.dir.y, r.dir.z, __uint_as_float(slabQ0 + q));
+                    }
+                    __syncwarp();
                 }
                 const uint32_t avail = slabEnd - slabCur;
                 const uint32_t rank = (uint32_t)__popc(need & ltMask);
                 if (!st.active && rank < avail)
                 {
-                    const uint32_t q = slabCur + rank;
-                    int x = slabX0 + (int)q, ri = slabRi0;
-                    while (x >= p.width) { x -= p.width; ++ri; }
-                    const int y = p.row0 + ri * p.rowStep;
-                    st.rng = pixel_seed((uint32_t)(y * p.width + x) * (uint32_t)p.spp + slabSample, slabFrame);
-                    float u = ((float)x + RandomFloat01(st.rng)) * p.invWidth;
-                    float v = ((float)y + RandomFloat01(st.rng)) * p.invHeight;
-                    Ray r = GetRay<false>(p.cam, u, v, st.rng);
-                    st.o = r.orig; st.d = r.dir;
+                    const float4 e0 = sRays[threadIdx.x >> 5][slabCur + rank][0];
+                    const float4 e1 = sRays[threadIdx.x >> 5][slabCur + rank][1];
+                    st.o = v3(e0.x, e0.y, e0.z); st.d = v3(e1.x, e1.y, e1.z);
+                    st.rng = __float_as_uint(e0.w);
+                    st.pixOff = __float_as_uint(e1.w);      // pixel index inside the tile
                     st.thr = v3(1, 1, 1); st.col = v3(0, 0, 0);
-                    st.pixOff = slabQ0 + q;                 // pixel index inside the tile
                     st.weight = slabW;
                     st.kind = 0; st.depth = 0; st.doMaterialE = true; st.active = true;
                 }
