@@ -115,3 +115,21 @@ def test_host_band_pipelining_equals_single_launch(gpu_ctx):
     assert outs[0][1] == outs[1][1] == outs[2][1]
     assert rel_l2(outs[1][0], outs[0][0]) < 1e-5 and rel_l2(outs[2][0], outs[0][0]) < 1e-5
     assert (outs[1][0][..., 3] == np.float32(0.25)).all()      # progressive: alpha preserved
+
+
+def test_expanded_form_sweep_matches_reference_form(gpu_ctx):
+    """The fast kernels' 8-slot expanded-form discriminant (FastHitterK) against the reference-form sweep on the SAME
+    per-path RNG streams: paths only differ where a rounding flips a hit decision, so the two images must agree far
+    below the Monte-Carlo noise (which would be ~2.4e-2 at 64 spp) and the ray counts within 1e-4."""
+    sph, mats, cam, em = golden_scene()
+    gpu_ctx.set_scene(sph, mats, cam, em)
+    gpu_ctx.set_option("fast_variant", 3)
+    out = []
+    for k in (1, 0):
+        gpu_ctx.set_option("fast_kform", k)
+        img = np.zeros((H, W, 4), np.float32)
+        rays = gpu_ctx.draw(0, 16, W, H, img, flags=2, mode=1)
+        out.append((img, rays))
+    gpu_ctx.set_option("fast_kform", 1)
+    assert abs(out[0][1] / out[1][1] - 1) < 1e-4
+    assert rel_l2(out[0][0], out[1][0]) < 3e-3

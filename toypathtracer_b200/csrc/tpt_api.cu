@@ -216,6 +216,7 @@ int tpt_set_option(tpt_context* ctx, const char* key, int value)
     if (!strcmp(key, "fast_variant")) { if (value < 0 || value > 7) return fail_msg(ctx, "fast_variant: 0..7"); ctx->fastVariant = value; return 0; }
     if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 8 && value != 32) return fail_msg(ctx, "exact_lanes: 0,1,8,32"); ctx->exactLanes = value; return 0; }
     if (!strcmp(key, "register_host")) { ctx->registerHost = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "fast_kform")) { fast_set_kform(value != 0); return 0; }
     if (!strcmp(key, "host_bands")) { if (value < 1 || value > tpt_context::kMaxBands) return fail_msg(ctx, "host_bands: 1..8"); ctx->hostBands = value; return 0; }
     if (!strcmp(key, "max_scratch_mb")) { if (value < 16) return fail_msg(ctx, "max_scratch_mb: >= 16"); ctx->maxScratchBytes = (size_t)value << 20; return 0; }
     return fail_msg(ctx, "tpt_set_option: unknown key");

@@ -365,11 +365,91 @@ struct QPath
     bool active;
 };
 
+// Fast-mode sweep in expanded form: with od = o.d, oo = o.o and K = |s|^2 - r^2 (per sphere, computed once per CTA in
+// double precision) nb = s.d - od and c = K + oo - 2 s.o, i.e. 8 instead of 10 FP32 issue slots per (ray, sphere):
+//   nb = fma(sx,dx, fma(sy,dy, fma(sz,dz, -od)));  c = fma(sx,-2ox, fma(sy,-2oy, fma(sz,-2oz, K+oo)));  discr = fma(nb,nb,-c)
+// Same two-pass structure and the same behind-the-origin rejection as SerialHitter. Algebraically the reference's
+// test (Maths.cpp:97-102); rounding differs (c loses ~|s|^2 * 2^-24 absolute accuracy), which the fast mode's
+// statistical tests bound. Padded "impossible" spheres get K = +1e30 so they can never be candidates here.
+struct FastHitterK
+{
+    uint32_t sphK;      // shared-memory address of {sx, sy, sz, K}[simdCount]
+    int simdCount;
+    __device__ __forceinline__ float4 ld(int i) const
+    {
+        float4 r;
+        asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(sphK + (uint32_t)i * 16u));
+        return r;
+    }
+    __device__ __forceinline__ int hit(const SceneView&, V3 o, V3 d, float tMin, float tMax, float& tOut) const
+    {
+        const float nod = -fmaf(o.x, d.x, fmaf(o.y, d.y, o.z * d.z));
+        const float oo = fmaf(o.x, o.x, fmaf(o.y, o.y, o.z * o.z));
+        const float ax = -2.0f * o.x, ay = -2.0f * o.y, az = -2.0f * o.z;
+        float bestT = tMax;
+        int bestId = -1;
+        for (int base = 0; base < simdCount; base += 32)
+        {
+            const int n = simdCount - base < 32 ? simdCount - base : 32;
+            uint32_t neg = 0;
+#pragma unroll
+            for (int k = 0; k < 32; k += 4)
+            {
+                if (k < n)
+                {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                    {
+                        const float4 s = ld(base + k + j);
+                        const float nb = fmaf(s.x, d.x, fmaf(s.y, d.y, fmaf(s.z, d.z, nod)));
+                        const float c = fmaf(s.x, ax, fmaf(s.y, ay, fmaf(s.z, az, s.w + oo)));
+                        const float discr = fmaf(nb, nb, -c);
+                        // reject: discr < 0, or centre behind (nb < 0) with the origin outside (c > 0)
+                        const uint32_t rej = __float_as_uint(discr) | (__float_as_uint(nb) & ~__float_as_uint(c));
+                        neg = __funnelshift_l(rej, neg, 1);
+                    }
+                }
+            }
+            uint32_t cand = ~neg & (n == 32 ? 0xffffffffu : ((1u << n) - 1u));
+            while (cand)
+            {
+                const int bit = 31 - __clz((int)cand);
+                cand &= ~(1u << bit);
+                const int i = base + (n - 1 - bit);
+                const float4 s = ld(i);
+                const float nb = fmaf(s.x, d.x, fmaf(s.y, d.y, fmaf(s.z, d.z, nod)));
+                const float c = fmaf(s.x, ax, fmaf(s.y, ay, fmaf(s.z, az, s.w + oo)));
+                const float discr = fmaf(nb, nb, -c);
+                if (discr > 0.0f)
+                {
+                    const float sq = M<false>::sqrt_(discr);
+                    float t = nb - sq;
+                    if (t <= tMin) t = nb + sq;
+                    if (t > tMin && t < bestT) { bestT = t; bestId = i; }
+                }
+            }
+        }
+        tOut = bestT;
+        return bestId;
+    }
+};
+
+// Builds {s, K} for every staged sphere (one CTA-wide pass, double precision for the cancellation |s|^2 - r^2).
+__device__ __forceinline__ void build_sphK(const SceneView& sc, float4* dst)
+{
+    for (int i = threadIdx.x; i < sc.simdCount; i += blockDim.x)
+    {
+        const Q4 s = ld_sph(sc, i);
+        const double K = (double)s.x * s.x + (double)s.y * s.y + (double)s.z * s.z - (double)s.w;
+        dst[i] = make_float4(s.x, s.y, s.z, i < sc.count ? (float)K : 1.0e30f);
+    }
+}
+
 // One iteration of the per-lane path state machine shared by the queue kernels: intersect the lane's current ray
 // (path or shadow) against all spheres, then shade. Returns true when the lane's path has ended (st.col is final).
-__device__ __forceinline__ bool path_step(const SceneView& sc, QPath& st, unsigned& rc)
+template <class Hitter>
+__device__ __forceinline__ bool path_step(const SceneView& sc, QPath& st, unsigned& rc, const Hitter& hitter)
 {
-    SerialHitter<false> hitter;
     // ---- intersect
     float t = TPT_MAX_T;
     int id = -1;
@@ -483,7 +563,7 @@ __device__ __forceinline__ bool path_step(const SceneView& sc, QPath& st, unsign
     return finished;
 }
 
-template <int MINB>
+template <int MINB, bool KFORM>
 __global__ void __launch_bounds__(kQueueThreads, MINB)
 k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights,
              uint32_t stagedBytes, uint32_t numSlabs, uint32_t S)
@@ -496,8 +576,12 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
     __shared__ float4 sRays[kQueueThreads / 32][kSlabPix][2];
     stage_blob(smem, blob, stagedBytes, &bar);
     if (threadIdx.x == 0) { float wp; blend_weights(p, sW, wp); }
-    __syncthreads();
     SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
+    float4* sphK = reinterpret_cast<float4*>(smem + ((stagedBytes + 15u) & ~15u));
+    if (KFORM) build_sphK(sc, sphK);
+    __syncthreads();
+    FastHitterK hitK; hitK.sphK = smem_u32(sphK); hitK.simdCount = sc.simdCount;
+    SerialHitter<false> hitS;
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
     const uint32_t regionPix = (uint32_t)((long long)p.numRows * p.width);
@@ -571,7 +655,7 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
         }
         if (!__any_sync(0xffffffffu, st.active)) break;
 
-        const bool finished = path_step(sc, st, rc);
+        const bool finished = KFORM ? path_step(sc, st, rc, hitK) : path_step(sc, st, rc, hitS);
         if (finished)
         {
             red_add_f4(p.image + (size_t)st.pixOff * 4, st.col.x * st.weight, st.col.y * st.weight, st.col.z * st.weight);
@@ -591,7 +675,7 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
 // S = spp x frames >= 16 the per-tile tail is < 1 %, at S = 4 variant 3 is the better choice.
 constexpr int kTileQPix = 1024;
 
-template <int MINB>
+template <int MINB, bool KFORM>
 __global__ void __launch_bounds__(kQueueThreads, MINB)
 k_fast_tileq(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights,
              uint32_t stagedBytes, uint32_t numTiles, uint32_t S, float wPrev, uint32_t tileQPix)
@@ -606,6 +690,10 @@ k_fast_tileq(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
     if (threadIdx.x == 0) { float wp; blend_weights(p, sW, wp); }
     for (int i = threadIdx.x; i < kTileQPix * 3; i += kQueueThreads) sAcc[i] = 0.0f;
     SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
+    float4* sphK = reinterpret_cast<float4*>(smem + ((stagedBytes + 15u) & ~15u));
+    if (KFORM) build_sphK(sc, sphK);
+    FastHitterK hitK; hitK.sphK = smem_u32(sphK); hitK.simdCount = sc.simdCount;
+    SerialHitter<false> hitS;
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
     const uint32_t regionPix = (uint32_t)((long long)p.numRows * p.width);
@@ -686,7 +774,7 @@ k_fast_tileq(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
                 need = __ballot_sync(0xffffffffu, !st.active);
             }
             if (!__any_sync(0xffffffffu, st.active)) break;
-            if (path_step(sc, st, rc))
+            if (KFORM ? path_step(sc, st, rc, hitK) : path_step(sc, st, rc, hitS))
             {
                 atomicAdd(&sAcc[st.pixOff * 3 + 0], st.col.x * st.weight);
                 atomicAdd(&sAcc[st.pixOff * 3 + 1], st.col.y * st.weight);
@@ -1042,8 +1130,13 @@ k_fast_wave(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayou
     if (lane == 0 && rc) atomicAdd(p.rayCounter, (unsigned long long)rc);
 }
 
+bool g_disableKForm = false;
+void fast_set_kform(bool enabled) { g_disableKForm = !enabled; }
+
 int fast_kernel_launches(const DrawParams&, int variant) { return (variant == 3 || variant == 4 || variant == 6 || variant == 7) ? 2 : 1; }
 
+
+extern bool g_disableKForm;
 
 cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, int numSMs, cudaStream_t stream)
 {
@@ -1077,11 +1170,15 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
     }
     if (variant == 3 || variant == 4)
     {
-        auto kern = variant == 3 ? k_fast_queue<6> : k_fast_queue<8>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc.stagedBytes);
+        // expanded-form sweep (8 FP32 slots/test) needs 16 B/sphere more shared memory: small scenes only
+        const int simdCount = (sc.count + 3) / 4 * 4;
+        const bool kform = simdCount <= 512 && !g_disableKForm;
+        auto kern = variant == 3 ? (kform ? k_fast_queue<6, true> : k_fast_queue<6, false>) : (kform ? k_fast_queue<8, true> : k_fast_queue<8, false>);
+        const size_t dyn3 = ((sc.stagedBytes + 15u) & ~15u) + (kform ? (size_t)simdCount * 16 : 0);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn3);
         if (e != cudaSuccess) return e;
         int perSM = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kQueueThreads, sc.stagedBytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kQueueThreads, dyn3);
         if (e != cudaSuccess) return e;
         if (perSM < 1) perSM = 1;
         float wPrev = 1.0f;
@@ -1098,8 +1195,8 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
         if (grid > warpsNeeded) grid = warpsNeeded;
         e = cudaMemsetAsync(p.workCounter, 0, sizeof(unsigned int), stream);
         if (e != cudaSuccess) return e;
-        kern<<<(unsigned)grid, kQueueThreads, sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes,
-                                                                      (uint32_t)slabs, S);
+        kern<<<(unsigned)grid, kQueueThreads, dyn3, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes,
+                                                                (uint32_t)slabs, S);
         return cudaGetLastError();
     }
     if (variant == 6 || variant == 7)
@@ -1135,11 +1232,14 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
     }
     if (variant == 5)
     {
-        auto kern = k_fast_tileq<6>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc.stagedBytes);
+        const int simdCount = (sc.count + 3) / 4 * 4;
+        const bool kform = simdCount <= 512 && !g_disableKForm;
+        auto kern = kform ? k_fast_tileq<6, true> : k_fast_tileq<6, false>;
+        const size_t dyn5 = ((sc.stagedBytes + 15u) & ~15u) + (kform ? (size_t)simdCount * 16 : 0);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn5);
         if (e != cudaSuccess) return e;
         int perSM = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kQueueThreads, sc.stagedBytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kQueueThreads, dyn5);
         if (e != cudaSuccess) return e;
         if (perSM < 1) perSM = 1;
         float wPrev = 1.0f;
@@ -1157,8 +1257,8 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
         if (grid > tiles) grid = tiles;
         e = cudaMemsetAsync(p.workCounter, 0, sizeof(unsigned int), stream);
         if (e != cudaSuccess) return e;
-        kern<<<(unsigned)grid, kQueueThreads, sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes,
-                                                                      (uint32_t)tiles, S, wPrev, tileQPix);
+        kern<<<(unsigned)grid, kQueueThreads, dyn5, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes,
+                                                                (uint32_t)tiles, S, wPrev, tileQPix);
         return cudaGetLastError();
     }
     return cudaErrorInvalidValue;

@@ -19,5 +19,6 @@ cudaError_t launch_debug_libm(int fn, const float* dIn, float* dOut, long long n
 // variant: see tpt_fast.cu
 cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, int numSMs, cudaStream_t stream);
 int fast_kernel_launches(const DrawParams& p, int variant);
+void fast_set_kform(bool enabled);   // expanded-form sphere sweep (default on for <= 512 spheres)
 
 } // namespace tpt
