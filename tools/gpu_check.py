@@ -26,7 +26,7 @@ log(f"libm powf(x,5): mismatches {bad.sum()} of {x.size}")
 
 # exact: frame 0..1 at 1280x720 vs reference, all lane configs
 rbuf, rrays = pyoracle.ref_render(w, h, 0, 2, flags=2)
-for lanes in (32,):
+for lanes in (32, 8, 1):
     ctx.set_option("exact_lanes", lanes)
     buf = np.zeros((h, w, 4), np.float32)
     t = time.time()
@@ -39,7 +39,7 @@ for lanes in (32,):
 
 # exact batched: 16 frames in one call vs reference progressive
 rbuf16, rrays16 = pyoracle.ref_render(w, h, 0, 16, flags=2)
-for lanes in (0,):
+for lanes in (0, 1, 8, 32):
     ctx.set_option("exact_lanes", lanes)
     buf = np.zeros((h, w, 4), np.float32)
     tot, pf = ctx.draw(0, 16, w, h, buf, flags=2, mode=tpt.MODE_EXACT, per_frame=True)
@@ -51,7 +51,7 @@ ctx.set_option("exact_lanes", 0)
 # fast variants
 import torch
 dbuf = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
-for var in (2, 3, 5, 6, 7):
+for var in (0, 2, 3, 5, 7):
     ctx.set_option("fast_variant", var)
     for rep in range(3):
         rays = ctx.draw(rep, 1, w, h, dbuf, flags=0, mode=tpt.MODE_FAST)

@@ -12,7 +12,7 @@ if scene == "ref":
 else:
     sph, mats, cam, em = tpt.stress_scene(w, h, int(scene))
 ctx.set_scene(sph, mats, cam, em)
-buf = np.zeros((h, w, 4), np.float32)
+buf = ctx.mem_alloc(w * h * 16)          # device-resident image: one kernel launch per draw (no host-band split)
 if mode == "fast":
     ctx.set_option("fast_variant", var)
     m = tpt.MODE_FAST
