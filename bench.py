@@ -41,6 +41,16 @@ SPHERES = 46
 FP32_TESTS_PER_S_PEAK = 148 * 128 * 1.965e9 / 17.0   # ~16 FP32 ops + compare per ray-sphere test, no FMA
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
+    (per launch, same workload); None when no capture of this round's kernel is committed."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01", "ncu_traffic.json")))
+        return t.get("k_fast_queue_1280x720_4spp_dram_bytes")
+    except Exception:
+        return None
+
+
 def load_peaks():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -281,7 +291,7 @@ def main():
                     "api": "tpt_set_scene + tpt_draw(host backbuffer) per step, wall clock"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": load_traffic() if args.mode == "fast" else None, "peak_source": peak_src,
                          "kernel": "k_fast_queue" if args.mode == "fast" else "k_trace_exact",
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "the path is FP32-issue bound, not HBM bound (SURVEY §8d): 16 B/pixel written per launch; "

@@ -191,3 +191,44 @@ def test_headless_shell_same_output_as_reference_build(libs):
     assert a.returncode == 0, a.stderr
     keep = lambda out: [l for l in out.splitlines() if l.startswith("frame") or l.startswith("checksum")]
     assert keep(a.stdout) == keep(b.stdout) and len(keep(a.stdout)) == 5
+
+
+def test_odd_sizes_and_single_row(gpu_ctx, oracle):
+    """Ragged shapes: odd width/height, one row, one column — exact mode vs the CPU restatement, all lane configs."""
+    sph, mats, cam0, em = golden_scene()
+    import toypathtracer_b200 as tpt
+    for (w, h) in [(97, 53), (33, 1), (1, 19), (130, 7)]:
+        cam = tpt.make_camera((0, 2, 3), (0, 0, 0), (0, 1, 0), 60, w / h, 0.02, 3)
+        gpu_ctx.set_scene(sph, mats, cam, em)
+        obuf, orays, pads = oracle.orc_render(sph, mats, cam, w, h, 2, 2, flags=2)
+        for lanes in (32, 8, 1):
+            gpu_ctx.set_option("exact_lanes", lanes)
+            buf = np.zeros((h, w, 4), np.float32)
+            total, pf = gpu_ctx.draw(2, 2, w, h, buf, flags=2, mode=0, per_frame=True)
+            assert pf == orays, (w, h, lanes)
+            assert not bits_differ(buf, obuf, pads).any(), (w, h, lanes)
+    gpu_ctx.set_option("exact_lanes", 0)
+
+
+def test_error_behaviour(libs):
+    """Every C-ABI call returns a status; bad arguments are refused with a message instead of rendering garbage."""
+    ctx = libs.Context(0)
+    buf = np.zeros((8, 8, 4), np.float32)
+    with pytest.raises(libs.TptError, match="no scene"):
+        ctx.draw(0, 1, 8, 8, buf)
+    sph, mats, cam, em = golden_scene()
+    ctx.set_scene(sph, mats, cam, em)
+    with pytest.raises(libs.TptError, match="rows outside"):
+        ctx.draw(0, 1, 8, 8, buf, rows=(4, 8, 1, 0))
+    with pytest.raises(libs.TptError, match="unknown mode"):
+        ctx.draw(0, 1, 8, 8, buf, mode=7)
+    with pytest.raises(libs.TptError, match="bad arguments"):
+        ctx.draw(0, 0, 8, 8, buf)
+    with pytest.raises(libs.TptError):
+        ctx.set_spp(0)
+    with pytest.raises(libs.TptError):
+        ctx.set_option("no_such_option", 1)
+    with pytest.raises(libs.TptError):
+        ctx.set_scene(sph[:0], mats[:0], cam, None)
+    assert ctx.draw(0, 1, 8, 8, buf) > 0           # still usable after the refusals
+    ctx.close()

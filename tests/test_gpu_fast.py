@@ -133,3 +133,20 @@ def test_expanded_form_sweep_matches_reference_form(gpu_ctx):
     gpu_ctx.set_option("fast_kform", 1)
     assert abs(out[0][1] / out[1][1] - 1) < 1e-4
     assert rel_l2(out[0][0], out[1][0]) < 3e-3
+
+
+def test_fast_odd_sizes_all_variants(gpu_ctx):
+    """Ragged shapes in the throughput kernels (tile / slab tails): finite image, sane rays per sample, every pixel hit."""
+    import toypathtracer_b200 as tpt
+    sph, mats, cam0, em = golden_scene()
+    for (w, h) in [(97, 53), (257, 3), (1, 130)]:
+        cam = tpt.make_camera((0, 2, 3), (0, 0, 0), (0, 1, 0), 60, w / h, 0.02, 3)
+        gpu_ctx.set_scene(sph, mats, cam, em)
+        for variant in VARIANTS:
+            gpu_ctx.set_option("fast_variant", variant)
+            img = np.full((h, w, 4), -1.0, np.float32)
+            rays = gpu_ctx.draw(0, 2, w, h, img, flags=0, mode=1)
+            assert np.isfinite(img).all() and (img[..., :3] >= 0).all(), (w, h, variant)
+            assert (img[..., :3].sum(axis=2) > 0).all(), (w, h, variant)      # sky/ground everywhere: no pixel skipped
+            assert 1.0 <= rays / (w * h * 4) < 12.0
+    gpu_ctx.set_option("fast_variant", 3)

@@ -374,6 +374,7 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
     ctx->haveTiming = true;
     k_accumulate_rays<<<1, 1, 0, stream>>>(ctx->dRayCounters, numFrames, ctx->dAccum);
     CK(cudaGetLastError(), "accumulate launch");
+    ctx->lastLaunches += 1;
 
     if (!bufferOnDevice && !pipelined)
         CK(cudaMemcpyAsync(backbuffer, dImage, bufBytes, cudaMemcpyDeviceToHost, stream), "D2H backbuffer");
