@@ -232,3 +232,24 @@ def test_error_behaviour(libs):
         ctx.set_scene(sph[:0], mats[:0], cam, None)
     assert ctx.draw(0, 1, 8, 8, buf) > 0           # still usable after the refusals
     ctx.close()
+
+
+def test_frame_batches_limited_by_scratch(gpu_ctx, oracle):
+    """numFrames larger than what the per-frame scratch may hold: the exact mode renders in several batches and the
+    progressive lerp still runs in reference order."""
+    sph, mats, cam, em = golden_scene()
+    gpu_ctx.set_scene(sph, mats, cam, em)
+    w, h = 192, 108
+    obuf, orays, pads = oracle.orc_render(sph, mats, cam, w, h, 0, 7, flags=2)
+    gpu_ctx.set_option("max_scratch_mb", 16)          # 192*108*16 B = 0.33 MB per frame -> plenty; then squeeze:
+    buf = np.zeros((h, w, 4), np.float32)
+    total, pf = gpu_ctx.draw(0, 7, w, h, buf, flags=2, mode=0, per_frame=True)
+    assert pf == orays and not bits_differ(buf, obuf, pads).any()
+    big_w, big_h = 1024, 1024                          # 16 MB per frame -> exactly one frame per batch at 16 MB
+    cam2 = __import__("toypathtracer_b200").make_camera((0, 2, 3), (0, 0, 0), (0, 1, 0), 60, 1.0, 0.02, 3)
+    gpu_ctx.set_scene(sph, mats, cam2, em)
+    o2, r2, p2 = oracle.orc_render(sph, mats, cam2, big_w, big_h, 0, 3, flags=2)
+    b2 = np.zeros((big_h, big_w, 4), np.float32)
+    t2, pf2 = gpu_ctx.draw(0, 3, big_w, big_h, b2, flags=2, mode=0, per_frame=True)
+    gpu_ctx.set_option("max_scratch_mb", 8192)
+    assert pf2 == r2 and not bits_differ(b2, o2, p2).any()

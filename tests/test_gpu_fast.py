@@ -150,3 +150,17 @@ def test_fast_odd_sizes_all_variants(gpu_ctx):
             assert (img[..., :3].sum(axis=2) > 0).all(), (w, h, variant)      # sky/ground everywhere: no pixel skipped
             assert 1.0 <= rays / (w * h * 4) < 12.0
     gpu_ctx.set_option("fast_variant", 3)
+
+
+def test_more_than_256_frames_in_one_call(gpu_ctx):
+    """Fast mode fuses at most 256 frames per launch; longer accumulations are chained launches with the same result as
+    two explicit calls."""
+    sph, mats, cam, em = golden_scene()
+    gpu_ctx.set_scene(sph, mats, cam, em)
+    gpu_ctx.set_option("fast_variant", 3)
+    w, h = 96, 54
+    one = np.zeros((h, w, 4), np.float32)
+    r1 = gpu_ctx.draw(0, 300, w, h, one, flags=2, mode=1)
+    two = np.zeros((h, w, 4), np.float32)
+    r2 = gpu_ctx.draw(0, 256, w, h, two, flags=2, mode=1) + gpu_ctx.draw(256, 44, w, h, two, flags=2, mode=1)
+    assert r1 == r2 and rel_l2(one, two) < 1e-5
