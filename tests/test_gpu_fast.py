@@ -100,21 +100,27 @@ def test_tonemap(gpu_ctx):
 
 
 def test_host_band_pipelining_equals_single_launch(gpu_ctx):
-    """Host-buffer draws are split into row bands on separate streams (D2H of a band overlaps tracing of the next);
-    the image must equal the unsplit draw (same per-pixel streams; only the order of the L2 reductions differs)."""
+    """Host-buffer draws overlap the D2H with tracing, either (a) with ONE kernel that publishes per-band completion
+    counters the copy stream waits on (cuStreamWaitValue32, `host_progress`), or (b) with one launch per row band on its
+    own stream (`host_bands`). Both must give the image of the plain draw (same per-pixel streams; only the order of the
+    L2 reductions differs) — and the progress path must never copy a band before its last path has landed."""
     sph, mats, cam, em = golden_scene()
     gpu_ctx.set_scene(sph, mats, cam, em)
     gpu_ctx.set_option("fast_variant", 3)
     outs = []
-    for bands in (1, 4, 7):
+    for (progress, pbands, bands) in [(0, 8, 1), (0, 8, 4), (0, 8, 7), (1, 1, 3), (1, 8, 3), (1, 16, 3)]:
+        gpu_ctx.set_option("host_progress", progress)
+        gpu_ctx.set_option("progress_bands", pbands)
         gpu_ctx.set_option("host_bands", bands)
-        img = np.full((H, W, 4), 0.25, np.float32)
-        rays = gpu_ctx.draw(5, 2, W, H, img, flags=2, mode=1)
-        outs.append((img, rays))
-    gpu_ctx.set_option("host_bands", 4)
-    assert outs[0][1] == outs[1][1] == outs[2][1]
-    assert rel_l2(outs[1][0], outs[0][0]) < 1e-5 and rel_l2(outs[2][0], outs[0][0]) < 1e-5
-    assert (outs[1][0][..., 3] == np.float32(0.25)).all()      # progressive: alpha preserved
+        for rep in range(3):                       # repeat: a too-early copy would be a race, not a constant error
+            img = np.full((H, W, 4), 0.25, np.float32)
+            rays = gpu_ctx.draw(5, 2, W, H, img, flags=2, mode=1)
+            outs.append((img, rays))
+    gpu_ctx.set_option("host_progress", 1); gpu_ctx.set_option("progress_bands", 8); gpu_ctx.set_option("host_bands", 3)
+    for img, rays in outs[1:]:
+        assert rays == outs[0][1]
+        assert rel_l2(img, outs[0][0]) < 1e-5
+        assert (img[..., 3] == np.float32(0.25)).all()      # progressive: alpha preserved
 
 
 def test_expanded_form_sweep_matches_reference_form(gpu_ctx):

@@ -5,6 +5,7 @@
 #include "tpt_scene_pack.h"
 #include "tpt_device_utils.cuh"
 #include "tpt_integrator.cuh"
+#include <cuda.h>      // types only: cuStreamWaitValue32 is resolved at run time (cudaGetDriverEntryPoint), libcuda is not linked
 #include <string>
 #include <vector>
 #include <string.h>
@@ -51,6 +52,15 @@ struct tpt_context
     cudaStream_t bandStream[kMaxBands] = {};
     cudaEvent_t bandEvent[kMaxBands] = {};
     cudaEvent_t forkEvent = nullptr;
+
+    // progress-triggered D2H (fast variant 3/4): the trace kernel publishes per-band completion counters, the copy
+    // stream waits on them with stream memory operations and copies a band while later bands are still being traced
+    typedef CUresult (*WaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    WaitValue32Fn waitValue32 = nullptr;
+    int hostProgress = 1;
+    int progressBands = 8;
+    unsigned int* dBandDone = nullptr;
+    cudaStream_t copyStream = nullptr;
 };
 
 static int fail(tpt_context* ctx, cudaError_t e, const char* what)
@@ -126,6 +136,16 @@ int tpt_create(int device, tpt_context** out)
     if (e == cudaSuccess) e = cudaMemset(ctx->dAccum, 0, 2 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->dWork, 64);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->forkEvent, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->dBandDone, 64);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking);
+    if (e == cudaSuccess)
+    {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            ctx->waitValue32 = (tpt_context::WaitValue32Fn)fn;
+        else (void)cudaGetLastError();
+    }
     int prLo = 0, prHi = 0;
     if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prLo, &prHi);   // prHi is the numerically smallest
     for (int b = 0; b < tpt_context::kMaxBands && e == cudaSuccess; ++b)
@@ -154,6 +174,8 @@ void tpt_destroy(tpt_context* ctx)
         if (ctx->bandEvent[b]) cudaEventDestroy(ctx->bandEvent[b]);
     }
     if (ctx->forkEvent) cudaEventDestroy(ctx->forkEvent);
+    if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+    cudaFree(ctx->dBandDone);
     if (ctx->evStart) cudaEventDestroy(ctx->evStart);
     if (ctx->evStop) cudaEventDestroy(ctx->evStop);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -217,6 +239,8 @@ int tpt_set_option(tpt_context* ctx, const char* key, int value)
     if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 8 && value != 32) return fail_msg(ctx, "exact_lanes: 0,1,8,32"); ctx->exactLanes = value; return 0; }
     if (!strcmp(key, "register_host")) { ctx->registerHost = value ? 1 : 0; return 0; }
     if (!strcmp(key, "fast_kform")) { fast_set_kform(value != 0); return 0; }
+    if (!strcmp(key, "host_progress")) { ctx->hostProgress = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "progress_bands")) { if (value < 1 || value > 16) return fail_msg(ctx, "progress_bands: 1..16"); ctx->progressBands = value; return 0; }
     if (!strcmp(key, "host_bands")) { if (value < 1 || value > tpt_context::kMaxBands) return fail_msg(ctx, "host_bands: 1..8"); ctx->hostBands = value; return 0; }
     if (!strcmp(key, "max_scratch_mb")) { if (value < 16) return fail_msg(ctx, "max_scratch_mb: >= 16"); ctx->maxScratchBytes = (size_t)value << 20; return 0; }
     return fail_msg(ctx, "tpt_set_option: unknown key");
@@ -318,7 +342,35 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
     // overlaps the tracing of band b+1 and the persistent CTAs of band b+1 fill the SMs as band b's tail drains.
     bool pipelined = mode == TPT_MODE_FAST && !bufferOnDevice && ctx->fastVariant >= 3 && ctx->fastVariant <= 7 && ctx->hostBands > 1 &&
                      (rowStep == 1 || packed) && framesPerLaunch == numFrames && numRows >= 16 * ctx->hostBands;
-    if (pipelined)
+    const bool progress = pipelined && ctx->waitValue32 && ctx->hostProgress && (ctx->fastVariant == 3 || ctx->fastVariant == 4);
+    if (progress)
+    {
+        // ONE kernel for the whole image; the copy stream waits on the kernel's per-band completion counters
+        const int NB = ctx->progressBands;
+        unsigned int expected[16];
+        CK(cudaMemsetAsync(ctx->dBandDone, 0, 64, stream), "zero band counters");
+        CK(cudaEventRecord(ctx->forkEvent, stream), "fork event");
+        CK(cudaStreamWaitEvent(ctx->copyStream, ctx->forkEvent, 0), "copy stream wait");
+        p.frame0 = frameCount; p.numFrames = numFrames; p.rayCounter = ctx->dRayCounters;
+        cudaError_t e = launch_fast(p, ctx->scene, ctx->fastVariant, ctx->numSMs, stream, ctx->dBandDone, NB, expected);
+        if (e != cudaSuccess) return fail(ctx, e, "kernel launch");
+        ctx->lastLaunches += fast_kernel_launches(p, ctx->fastVariant);
+        const long long regionPix = (long long)numRows * width, slab = fast_slab_pixels();
+        const long long mtiles = (regionPix + slab - 1) / slab, mpb = (mtiles + NB - 1) / NB;
+        const size_t firstPix = packed ? 0 : (size_t)row0 * width;
+        for (int b = 0; b < NB; ++b)
+        {
+            const long long p0 = (long long)b * mpb * slab, p1 = (long long)(b + 1) * mpb * slab < regionPix ? (long long)(b + 1) * mpb * slab : regionPix;
+            if (p1 <= p0) continue;
+            if (ctx->waitValue32((CUstream)ctx->copyStream, (CUdeviceptr)(ctx->dBandDone + b), expected[b], CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+                return fail_msg(ctx, "cuStreamWaitValue32 failed");
+            const size_t off = (firstPix + (size_t)p0) * 4;
+            CK(cudaMemcpyAsync(backbuffer + off, dImage + off, (size_t)(p1 - p0) * 16, cudaMemcpyDeviceToHost, ctx->copyStream), "D2H band");
+        }
+        CK(cudaEventRecord(ctx->bandEvent[0], ctx->copyStream), "copy event");
+        CK(cudaStreamWaitEvent(stream, ctx->bandEvent[0], 0), "join copies");
+    }
+    else if (pipelined)
     {
         const int NB = ctx->hostBands;
         CK(cudaEventRecord(ctx->forkEvent, stream), "fork event");

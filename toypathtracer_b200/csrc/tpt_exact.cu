@@ -28,8 +28,10 @@ __global__ void k_trace_exact(DrawParams p, const unsigned char* __restrict__ bl
     const long long chain = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
     const long long totalChains = (long long)p.numRows * p.numFrames;
     if (chain >= totalChains) return;
-    const int fi = (int)(chain / p.numRows);
-    const int ri = (int)(chain % p.numRows);
+    // consecutive chains = the same row in consecutive frames: neighbouring lanes trace the same pixels with different
+    // RNG streams (coherent geometry, similar path lengths), and the expensive bottom rows are scheduled first
+    const int ri = (int)(chain / p.numFrames);
+    const int fi = (int)(chain % p.numFrames);
     const int y = p.row0 + ri * p.rowStep;
     const int frame = p.frame0 + fi;
 

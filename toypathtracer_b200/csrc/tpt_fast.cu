@@ -534,8 +534,13 @@ __device__ __forceinline__ bool path_step(const SceneView& sc, QPath& st, unsign
             float d2 = dot(pc, pc);
             float inv = rsqrtf(d2);
             V3 sw = pc * inv;
-            V3 su = M<false>::normalize(cross(fabsf(sw.x) > 0.01f ? v3(0, 1, 0) : v3(1, 0, 0), sw));
-            V3 sv = cross(sw, su);
+            // any orthonormal (su, sv) around sw gives the same cone-sample distribution (phi is uniform): use the
+            // branch-free basis of Duff et al. 2017 instead of normalize(cross(up, sw)), cross(sw, su) (Test.cpp:108-109)
+            const float sgn = copysignf(1.0f, sw.z);
+            const float oa = -1.0f / (sgn + sw.z);
+            const float ob = sw.x * sw.y * oa;
+            V3 su = v3(1.0f + sgn * sw.x * sw.x * oa, sgn * ob, -sgn * sw.x);
+            V3 sv = v3(ob, sgn + sw.y * sw.y * oa, -sw.y);
             float cosAMax = M<false>::sqrt_(1.0f - Lr.radius * Lr.radius * inv * inv);
             float eps1 = RandomFloat01(st.rng), eps2 = RandomFloat01(st.rng);
             float cosA = 1.0f - eps1 + eps1 * cosAMax;
@@ -566,7 +571,7 @@ __device__ __forceinline__ bool path_step(const SceneView& sc, QPath& st, unsign
 template <int MINB, bool KFORM>
 __global__ void __launch_bounds__(kQueueThreads, MINB)
 k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights,
-             uint32_t stagedBytes, uint32_t numSlabs, uint32_t S)
+             uint32_t stagedBytes, uint32_t numSlabs, uint32_t S, unsigned int* __restrict__ bandDone, uint32_t mtilesPerBand)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
@@ -595,6 +600,13 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
     uint32_t slabSample = 0, slabFrame = 0;
     float slabW = 0.0f;
     bool exhausted = false;
+    // progress reporting for host-buffer draws (bandDone != nullptr): slabs are dealt in pixel order, so the image
+    // completes band by band; every lane counts the paths it finished per band and publishes the count (after a
+    // __threadfence so its reductions are visible first) when it moves on to the next band. The host's copy stream
+    // waits on these counters (cuStreamWaitValue32) and starts the D2H of a band while later bands are still traced.
+    uint32_t slabBand = 0;
+    int curBand = -1;
+    uint32_t doneCnt = 0, myBand = 0;
 
     QPath st;
     st.active = false;
@@ -620,6 +632,7 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
                 slabSample = s - fi * (uint32_t)p.spp;
                 slabFrame = (uint32_t)p.frame0 + fi;
                 slabW = invSpp * sW[fi];
+                slabBand = bandDone ? mtile / mtilesPerBand : 0u;
                 __syncwarp();       // every lane has popped what it needed from the previous slab
                 for (uint32_t q = (uint32_t)lane; q < slabEnd; q += 32)
                 {
@@ -647,6 +660,7 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
                 st.pixOff = __float_as_uint(e1.w);
                 st.thr = v3(1, 1, 1); st.col = v3(0, 0, 0);
                 st.weight = slabW;
+                myBand = slabBand;
                 st.kind = 0; st.depth = 0; st.doMaterialE = true; st.active = true;
             }
             const uint32_t n = (uint32_t)__popc(need);
@@ -660,8 +674,18 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
         {
             red_add_f4(p.image + (size_t)st.pixOff * 4, st.col.x * st.weight, st.col.y * st.weight, st.col.z * st.weight);
             st.active = false;
+            if (bandDone)
+            {
+                if ((int)myBand != curBand)
+                {
+                    if (doneCnt) { __threadfence(); atomicAdd(bandDone + curBand, doneCnt); }
+                    curBand = (int)myBand; doneCnt = 0;
+                }
+                ++doneCnt;
+            }
         }
     }
+    if (bandDone && doneCnt) { __threadfence(); atomicAdd(bandDone + curBand, doneCnt); }
     for (int off = 16; off > 0; off >>= 1) rc += __shfl_xor_sync(0xffffffffu, rc, off);
     if (lane == 0 && rc) atomicAdd(p.rayCounter, (unsigned long long)rc);
 }
@@ -1130,6 +1154,7 @@ k_fast_wave(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayou
     if (lane == 0 && rc) atomicAdd(p.rayCounter, (unsigned long long)rc);
 }
 
+int fast_slab_pixels() { return kSlabPix; }
 bool g_disableKForm = false;
 void fast_set_kform(bool enabled) { g_disableKForm = !enabled; }
 
@@ -1138,7 +1163,8 @@ int fast_kernel_launches(const DrawParams&, int variant) { return (variant == 3 
 
 extern bool g_disableKForm;
 
-cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, int numSMs, cudaStream_t stream)
+cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, int numSMs, cudaStream_t stream,
+                        unsigned int* bandDone, int numBands, unsigned int* bandExpected)
 {
     if (p.numFrames > kMaxFramesPerDraw) return cudaErrorInvalidValue;
     cudaError_t e;
@@ -1195,8 +1221,21 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
         if (grid > warpsNeeded) grid = warpsNeeded;
         e = cudaMemsetAsync(p.workCounter, 0, sizeof(unsigned int), stream);
         if (e != cudaSuccess) return e;
+        // optional progress bands (host-buffer draws): band b = macro-tiles [b*mpb, (b+1)*mpb)
+        const uint32_t mtiles = (uint32_t)((regionPix + kSlabPix - 1) / kSlabPix);
+        uint32_t mpb = 0;
+        if (bandDone && numBands > 0)
+        {
+            mpb = (mtiles + (uint32_t)numBands - 1) / (uint32_t)numBands;
+            for (int b = 0; b < numBands; ++b)
+            {
+                const long long p0 = (long long)b * mpb * kSlabPix, p1 = (long long)(b + 1) * mpb * kSlabPix;
+                const long long px = (p1 < regionPix ? p1 : regionPix) - (p0 < regionPix ? p0 : regionPix);
+                bandExpected[b] = (unsigned int)(px * S);
+            }
+        }
         kern<<<(unsigned)grid, kQueueThreads, dyn3, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes,
-                                                                (uint32_t)slabs, S);
+                                                                (uint32_t)slabs, S, mpb ? bandDone : nullptr, mpb ? mpb : 1u);
         return cudaGetLastError();
     }
     if (variant == 6 || variant == 7)

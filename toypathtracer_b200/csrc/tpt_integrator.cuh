@@ -145,6 +145,14 @@ template <bool EXACT> TPT_HD V3 RandomUnitVector(uint32_t& state)
     float z = RandomFloat01(state) * 2.0f - 1.0f;
     float a = RandomFloat01(state) * 2.0f * TPT_PI;
     float r = M<EXACT>::sqrt_(1.0f - z * z);
+#if defined(__CUDA_ARCH__)
+    if (!EXACT)
+    {
+        float sa, ca;
+        __sincosf(a, &sa, &ca);
+        return v3(r * ca, r * sa, z);
+    }
+#endif
     float x = r * M<EXACT>::cos_(a);
     float y = r * M<EXACT>::sin_(a);
     return v3(x, y, z);

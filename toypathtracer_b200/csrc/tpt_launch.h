@@ -17,7 +17,12 @@ struct SceneDev
 cudaError_t launch_exact(const DrawParams& p, const SceneDev& sc, int lanes, cudaStream_t stream);
 cudaError_t launch_debug_libm(int fn, const float* dIn, float* dOut, long long n, cudaStream_t stream);
 // variant: see tpt_fast.cu
-cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, int numSMs, cudaStream_t stream);
+// bandDone (optional, variant 3/4 only): device counters [numBands]; the kernel publishes finished paths per band of
+// macro-tiles, bandExpected[b] receives the final count of band b (host array) and kSlabPix*ceil(mtiles/numBands) pixels
+// form a band.
+cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, int numSMs, cudaStream_t stream,
+                        unsigned int* bandDone = nullptr, int numBands = 0, unsigned int* bandExpected = nullptr);
+int fast_slab_pixels();
 int fast_kernel_launches(const DrawParams& p, int variant);
 void fast_set_kform(bool enabled);   // expanded-form sphere sweep (default on for <= 512 spheres)
 
