@@ -211,6 +211,9 @@ def main():
 
     for s in range(args.warmup):
         step(s)
+    if world > 1:
+        dist.all_reduce(image, op=dist.ReduceOp.SUM)                      # warm-up includes the exchange step (NCCL sets up
+        dist.all_reduce(image, op=dist.ReduceOp.SUM)                      # its buffers / NVLS on the first large collective)
     ctx.read_ray_count(sh)                                                # reset the accumulated counter
     torch.cuda.synchronize(dev)
     if world > 1:
