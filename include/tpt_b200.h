@@ -105,6 +105,9 @@ int tpt_ipc_close(tpt_context* ctx, void* devPtr);
 /* Diagnostic used by the parity tests: evaluates the device-side libm restatement the exact mode uses
  * (toypathtracer_b200/csrc/tpt_libm.cuh) on n host floats. fn: 0 = sinf, 1 = cosf, 2 = powf(x, 5). */
 int tpt_debug_libm(tpt_context* ctx, int fn, const float* in, float* out, long long n);
+/* Diagnostic: device timestamps (ms since the start of the last progress-mode host draw) of the trace kernel's end,
+ * each band copy's end and the draw's end. Returns minus the number of entries written. */
+int tpt_debug_timeline(tpt_context* ctx, float* outMs, int capacity);
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,9 @@ struct tpt_context
     int progressBands = 8;
     unsigned int* dBandDone = nullptr;
     cudaStream_t copyStream = nullptr;
+    // diagnostics: timestamps of the last progress-mode draw (kernel end, each band copy end), see tpt_debug_timeline
+    cudaEvent_t tlKernelEnd = nullptr, tlBand[16] = {};
+    int tlBands = 0;
 };
 
 static int fail(tpt_context* ctx, cudaError_t e, const char* what)
@@ -137,6 +140,8 @@ int tpt_create(int device, tpt_context** out)
     if (e == cudaSuccess) e = cudaMalloc(&ctx->dWork, 64);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->forkEvent, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->dBandDone, 64);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->tlKernelEnd);
+    for (int b = 0; b < 16 && e == cudaSuccess; ++b) e = cudaEventCreate(&ctx->tlBand[b]);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking);
     if (e == cudaSuccess)
     {
@@ -355,6 +360,8 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
         cudaError_t e = launch_fast(p, ctx->scene, ctx->fastVariant, ctx->numSMs, stream, ctx->dBandDone, NB, expected);
         if (e != cudaSuccess) return fail(ctx, e, "kernel launch");
         ctx->lastLaunches += fast_kernel_launches(p, ctx->fastVariant);
+        CK(cudaEventRecord(ctx->tlKernelEnd, stream), "timeline event");
+        ctx->tlBands = 0;
         const long long regionPix = (long long)numRows * width, slab = fast_slab_pixels();
         const long long mtiles = (regionPix + slab - 1) / slab, mpb = (mtiles + NB - 1) / NB;
         const size_t firstPix = packed ? 0 : (size_t)row0 * width;
@@ -366,6 +373,7 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
                 return fail_msg(ctx, "cuStreamWaitValue32 failed");
             const size_t off = (firstPix + (size_t)p0) * 4;
             CK(cudaMemcpyAsync(backbuffer + off, dImage + off, (size_t)(p1 - p0) * 16, cudaMemcpyDeviceToHost, ctx->copyStream), "D2H band");
+            CK(cudaEventRecord(ctx->tlBand[ctx->tlBands++], ctx->copyStream), "timeline event");
         }
         CK(cudaEventRecord(ctx->bandEvent[0], ctx->copyStream), "copy event");
         CK(cudaStreamWaitEvent(stream, ctx->bandEvent[0], 0), "join copies");
@@ -560,6 +568,23 @@ int tpt_ipc_close(tpt_context* ctx, void* devPtr)
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     CK(cudaIpcCloseMemHandle(devPtr), "cudaIpcCloseMemHandle");
     return 0;
+}
+
+int tpt_debug_timeline(tpt_context* ctx, float* outMs, int capacity)
+{
+    if (!ctx || !outMs || capacity < 1) return (int)cudaErrorInvalidValue;
+    CK(cudaEventSynchronize(ctx->evStop), "event sync");
+    int n = 0;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->evStart, ctx->tlKernelEnd), "elapsed");
+    outMs[n++] = ms;
+    for (int b = 0; b < ctx->tlBands && n < capacity; ++b)
+    {
+        CK(cudaEventElapsedTime(&ms, ctx->evStart, ctx->tlBand[b]), "elapsed");
+        outMs[n++] = ms;
+    }
+    if (n < capacity) { CK(cudaEventElapsedTime(&ms, ctx->evStart, ctx->evStop), "elapsed"); outMs[n++] = ms; }
+    return -n;   // negative count = number of entries written
 }
 
 int tpt_debug_libm(tpt_context* ctx, int fn, const float* in, float* out, long long n)
