@@ -137,7 +137,7 @@ int tpt_create(int device, tpt_context** out)
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->evStop);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->dAccum, 2 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(ctx->dAccum, 0, 2 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->dWork, 64);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->dWork, 256);   // 4 uints per concurrent launch (tile/slab, front, back cursors)
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->forkEvent, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->dBandDone, 64);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->tlKernelEnd);
@@ -391,7 +391,7 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
             DrawParams pb = p;
             pb.row0 = row0 + rb0 * rowStep;
             pb.numRows = rb1 - rb0;
-            pb.workCounter = ctx->dWork + b;
+            pb.workCounter = ctx->dWork + 4 * b;
             const size_t firstRow = packed ? (size_t)rb0 : (size_t)(row0 + rb0);   // rowStep == 1 when not packed
             if (packed) pb.image = dImage + firstRow * width * 4;
             cudaError_t e = launch_fast(pb, ctx->scene, ctx->fastVariant, ctx->numSMs, bs);
