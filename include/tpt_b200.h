@@ -57,7 +57,7 @@ int tpt_set_spp(tpt_context* ctx, int spp);
  * reference shell's does; default 0 — buffers that are already pinned are detected by CUDA on their own), "host_bands" (1..8, default 3:
  * host-buffer fast draws are split into row bands on separate streams so the D2H of one band overlaps the tracing of
  * the next), "host_progress" (default 1: with fast variant 3/4 a single kernel publishes per-band completion counters and the
- * copy stream waits on them with cuStreamWaitValue32, "progress_bands" bands, default 8; 0 falls back to host_bands). */
+ * copy stream waits on them with cuStreamWaitValue32, "progress_bands" bands, default 4; 0 falls back to host_bands). */
 int tpt_set_option(tpt_context* ctx, const char* key, int value);
 
 /* Replaces DrawTest() (Test.cpp:344-367) for frames [frameCount, frameCount+numFrames) — numFrames*spp samples

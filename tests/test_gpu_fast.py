@@ -116,7 +116,7 @@ def test_host_band_pipelining_equals_single_launch(gpu_ctx):
             img = np.full((H, W, 4), 0.25, np.float32)
             rays = gpu_ctx.draw(5, 2, W, H, img, flags=2, mode=1)
             outs.append((img, rays))
-    gpu_ctx.set_option("host_progress", 1); gpu_ctx.set_option("progress_bands", 8); gpu_ctx.set_option("host_bands", 3)
+    gpu_ctx.set_option("host_progress", 1); gpu_ctx.set_option("progress_bands", 4); gpu_ctx.set_option("host_bands", 3)
     for img, rays in outs[1:]:
         assert rays == outs[0][1]
         assert rel_l2(img, outs[0][0]) < 1e-5

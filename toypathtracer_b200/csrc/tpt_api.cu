@@ -58,7 +58,7 @@ struct tpt_context
     typedef CUresult (*WaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
     WaitValue32Fn waitValue32 = nullptr;
     int hostProgress = 1;
-    int progressBands = 8;
+    int progressBands = 4;
     unsigned int* dBandDone = nullptr;
     cudaStream_t copyStream = nullptr;
     // diagnostics: timestamps of the last progress-mode draw (kernel end, each band copy end), see tpt_debug_timeline
@@ -365,7 +365,7 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
         const long long regionPix = (long long)numRows * width, slab = fast_slab_pixels();
         const long long mtiles = (regionPix + slab - 1) / slab, mpb = (mtiles + NB - 1) / NB;
         const size_t firstPix = packed ? 0 : (size_t)row0 * width;
-        for (int b = 0; b < NB; ++b)
+        for (int b = NB - 1; b >= 0; --b)     // the kernel walks the image from its last macro-tile down: last band first
         {
             const long long p0 = (long long)b * mpb * slab, p1 = (long long)(b + 1) * mpb * slab < regionPix ? (long long)(b + 1) * mpb * slab : regionPix;
             if (p1 <= p0) continue;

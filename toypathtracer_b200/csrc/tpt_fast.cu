@@ -604,8 +604,9 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
     // completes band by band; every lane counts the paths it finished per band and publishes the count (after a
     // __threadfence so its reductions are visible first) when it moves on to the next band. The host's copy stream
     // waits on these counters (cuStreamWaitValue32) and starts the D2H of a band while later bands are still traced.
-    // (Measured: band 0 of 8 completes at ~55 % of the kernel, not 12 % — warps progress unevenly — so about half of the
-    // copy overlaps; dealing slabs from both ends of the image by hardware warp slot was tried and made it worse.)
+    // (Measured: whichever band is dealt first completes at ~50 % of the kernel, not at 1/bands — warps progress
+    // unevenly and a few keep their first slab for a long time — so about half of the copy overlaps; dealing slabs from
+    // both ends of the image by hardware warp slot, and cheap-rows-first ordering, did not change that.)
     uint32_t slabBand = 0;
     int curBand = -1;
     uint32_t doneCnt = 0, myBand = 0;
@@ -624,7 +625,12 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
                 if (lane == 0) slab = atomicAdd(p.workCounter, 1u);
                 slab = __shfl_sync(0xffffffffu, slab, 0);
                 if (slab >= numSlabs) { exhausted = true; break; }
-                const uint32_t mtile = slab / S, s = slab - mtile * S;
+                uint32_t mtile = slab / S;
+                const uint32_t s = slab - mtile * S;
+                // progress mode: walk the image from its LAST macro-tile to its first. Row 0 is the bottom of the image
+                // (ground, light sampling: the expensive pixels); starting with the cheap upper rows makes pixels
+                // complete early at a high rate, so most of the D2H runs under the expensive rows' tracing.
+                if (bandDone) mtile = (numSlabs / S) - 1u - mtile;
                 const uint32_t pix0 = mtile * kSlabPix;
                 slabEnd = regionPix - pix0 < (uint32_t)kSlabPix ? regionPix - pix0 : (uint32_t)kSlabPix;
                 slabCur = 0;
