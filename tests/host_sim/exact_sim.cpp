@@ -55,3 +55,57 @@ extern "C" int sim_render_exact(const void* spheres, const void* mats, int count
     }
     return 0;
 }
+
+
+// Same, through the flat per-chain state machine (xchain_step) the batched LANES = 1 kernel uses.
+extern "C" int sim_render_exact_flat(const void* spheres, const void* mats, int count, const void* cam,
+                                     int w, int h, int frame0, int nframes, unsigned flags, int spp,
+                                     float* buf, long long* rays, int nthreads)
+{
+    std::vector<unsigned char> blob; SceneBlobLayout L; int nLights;
+    pack_scene_blob((const Sphere20*)spheres, (const Material36*)mats, count, nullptr, 0, blob, L, nLights);
+    SceneView sc = scene_view_from_blob(blob.data(), L, count, nLights);
+    Camera88 c; memcpy(&c, cam, sizeof(c));
+    float invW = 1.0f / w, invH = 1.0f / h;
+    if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
+    SerialHitter<true> hitter;
+    for (int f = 0; f < nframes; ++f)
+    {
+        int frame = frame0 + f;
+        float lerpFac = lerp_fac(frame, flags);
+        std::atomic<int> next(0);
+        std::atomic<long long> total(0);
+        auto work = [&]() {
+            long long mine = 0;
+            for (;;)
+            {
+                int y = next.fetch_add(1);
+                if (y >= h) break;
+                unsigned rc = 0;
+                XChain ch;
+                xchain_begin(ch, c, y, frame, invW, invH);
+                float* row = buf + (size_t)y * w * 4;
+                while (ch.x < w)
+                {
+                    V3 col;
+                    const int x = ch.x;
+                    if (xchain_step(sc, c, ch, y, spp, w, invW, invH, rc, hitter, col))
+                    {
+                        float* bb = row + (size_t)x * 4;
+                        V3 prev = v3(bb[0], bb[1], bb[2]);
+                        col = prev * lerpFac + col * (1.0f - lerpFac);
+                        bb[0] = col.x; bb[1] = col.y; bb[2] = col.z;
+                    }
+                }
+                mine += rc;
+            }
+            total += mine;
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthreads; ++t) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+        if (rays) rays[f] = total.load();
+    }
+    return 0;
+}

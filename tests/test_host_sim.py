@@ -11,13 +11,14 @@ from conftest import bits_differ
 from test_oracle import GOLD, golden_scene
 
 
-def sim_render(host_sim, sph, mats, cam, w, h, f0, nf, flags, spp=4):
+def sim_render(host_sim, sph, mats, cam, w, h, f0, nf, flags, spp=4, flat=False):
     L = host_sim["exact_sim"]
     buf = np.zeros((h, w, 4), np.float32)
     rays = (ctypes.c_longlong * nf)()
     vp = lambda a: np.ascontiguousarray(a).ctypes.data_as(ctypes.c_void_p)
     sph = np.ascontiguousarray(sph); mats = np.ascontiguousarray(mats); cam = np.ascontiguousarray(cam)
-    L.sim_render_exact(vp(sph), vp(mats), sph.nbytes // 20, vp(cam), w, h, f0, nf, ctypes.c_uint(flags), spp, vp(buf), rays, 0)
+    fn = L.sim_render_exact_flat if flat else L.sim_render_exact
+    fn(vp(sph), vp(mats), sph.nbytes // 20, vp(cam), w, h, f0, nf, ctypes.c_uint(flags), spp, vp(buf), rays, 0)
     return buf, [int(r) for r in rays]
 
 
@@ -36,3 +37,17 @@ def test_product_source_matches_oracle_on_runtime_scene(host_sim, oracle):
     buf, rays = sim_render(host_sim, sph, mats, cam, 160, 90, 3, 2, 2)
     assert rays == orays
     assert not bits_differ(buf, obuf, pads).any()
+
+
+def test_flat_state_machine_matches_golden_and_oracle(host_sim, oracle):
+    """xchain_step (one sweep per step; the batched LANES = 1 kernel's form) is bit-identical to the nested form."""
+    g = np.load(os.path.join(GOLD, "ref_192x108_f0-3.npz"))
+    sph, mats, cam, em = golden_scene()
+    buf, rays = sim_render(host_sim, sph, mats, cam, 192, 108, 0, 4, 2, flat=True)
+    assert rays == [int(r) for r in g["rays"]]
+    assert not bits_differ(buf, g["image"]).any()
+    import toypathtracer_b200 as tpt
+    s2, m2, c2, e2 = tpt.stress_scene(160, 90, count=203)
+    obuf, orays, pads = oracle.orc_render(s2, m2, c2, 160, 90, 3, 2, flags=2)
+    buf, rays = sim_render(host_sim, s2, m2, c2, 160, 90, 3, 2, 2, flat=True)
+    assert rays == orays and not bits_differ(buf, obuf, pads).any()

@@ -43,6 +43,9 @@ run("C2 46 spheres 1280x720 4spp", ref720, 1280, 720, 0, 1, 0, 1, reps=5)
 run("C2 46 spheres 1280x720 4spp", ref720, 1280, 720, 0, 1, 0, 0, reps=2, expect_rays=16809105, note="golden SURVEY 9.2")
 run("C2-correctness 1280x720 1024spp (256 frames, one call)", ref720, 1280, 720, 0, 256, 2, 0, reps=1, expect_rays=4304161180,
     note="golden SURVEY 9.2; bit-identical image checked in tests at smaller sizes and here by ray count")
+ctx.set_option("exact_lanes", 2)
+run("C2-correctness 1280x720 1024spp (256 frames, one call) [nested-loop form]", ref720, 1280, 720, 0, 256, 2, 0, reps=1, expect_rays=4304161180)
+ctx.set_option("exact_lanes", 0)
 run("C2-correctness 1280x720 1024spp", ref720, 1280, 720, 0, 256, 2, 1, reps=1)
 run("C3 46 spheres 3840x2160 16spp", ref4k, 3840, 2160, 0, 4, 2, 1, reps=3)
 run("C3 46 spheres 3840x2160 16spp", ref4k, 3840, 2160, 0, 4, 2, 0, reps=1, expect_rays=605318173, note="golden SURVEY 9.9")

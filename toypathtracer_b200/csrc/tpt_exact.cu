@@ -69,6 +69,54 @@ __global__ void k_trace_exact(DrawParams p, const unsigned char* __restrict__ bl
     if (sub == 0) atomicAdd(p.rayCounter + fi, (unsigned long long)rc);
 }
 
+// One thread per chain, flat form: every loop iteration is one xchain_step() = one sphere sweep, so the lanes of a
+// warp (the same row in 32 consecutive frames) stay converged on the sweep whatever their paths are doing.
+__global__ void __launch_bounds__(128)
+k_trace_exact_flat(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights, uint32_t stagedBytes)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    stage_blob(smem, blob, stagedBytes, &bar);
+    SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
+    const long long chain = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long totalChains = (long long)p.numRows * p.numFrames;
+    if (chain >= totalChains) return;
+    const int ri = (int)(chain / p.numFrames);
+    const int fi = (int)(chain % p.numFrames);
+    const int y = p.row0 + ri * p.rowStep;
+    const int frame = p.frame0 + fi;
+    const float lerpFac = lerp_fac(frame, p.flags);
+    const float oneMinus = 1.0f - lerpFac;
+    const size_t imgRow = (size_t)(p.packed ? ri : y) * p.width;
+    SerialHitter<true> hitter;
+    unsigned rc = 0;
+    XChain c;
+    xchain_begin(c, p.cam, y, frame, p.invWidth, p.invHeight);
+    while (c.x < p.width)
+    {
+        const int x = c.x;
+        V3 col;
+        if (xchain_step(sc, p.cam, c, y, p.spp, p.width, p.invWidth, p.invHeight, rc, hitter, col))
+        {
+            if (p.numFrames == 1)
+            {
+                float4* px = reinterpret_cast<float4*>(p.image + (imgRow + x) * 4);
+                float4 prev = *px;
+                prev.x = prev.x * lerpFac + col.x * oneMinus;
+                prev.y = prev.y * lerpFac + col.y * oneMinus;
+                prev.z = prev.z * lerpFac + col.z * oneMinus;
+                *px = prev;
+            }
+            else
+            {
+                float4* px = reinterpret_cast<float4*>(p.scratch) + ((size_t)fi * p.numRows + ri) * p.width + x;
+                *px = make_float4(col.x, col.y, col.z, 0.0f);
+            }
+        }
+    }
+    atomicAdd(p.rayCounter + fi, (unsigned long long)rc);
+}
+
 // Sequential progressive blend of the per-frame colours (Test.cpp:272-276,293-295), one thread per pixel,
 // frames in order so the float sequence is the reference's.
 __global__ void k_resolve_exact(DrawParams p)
@@ -134,7 +182,15 @@ cudaError_t launch_exact(const DrawParams& p, const SceneDev& sc, int lanes, cud
     const int block = threads >= 148LL * 256 ? 128 : (threads >= 148LL * 64 ? 64 : 32);
     switch (lanes)
     {
-    case 1: e = launch_exact_t<1>(p, sc, stream, block); break;
+    case 1:
+    {
+        e = cudaFuncSetAttribute(k_trace_exact_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc.stagedBytes);
+        if (e != cudaSuccess) return e;
+        k_trace_exact_flat<<<(unsigned)((totalChains + 127) / 128), 128, sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes);
+        e = cudaGetLastError();
+        break;
+    }
+    case 2: e = launch_exact_t<1>(p, sc, stream, block); break;      // nested-loop form, one lane per chain (kept for comparison)
     case 8: e = launch_exact_t<8>(p, sc, stream, block); break;
     case 32: e = launch_exact_t<32>(p, sc, stream, block); break;
     default: return cudaErrorInvalidValue;

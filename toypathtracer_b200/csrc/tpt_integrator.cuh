@@ -600,3 +600,133 @@ TPT_HD V3 pixel_exact(const SceneView& sc, const Camera88& cam, int x, int y, in
 }
 
 } // namespace tpt
+
+// ---- flat state machine of the exact path (one sphere sweep per step) ------------------------------------------------
+// Same arithmetic and the same RNG draw order as pixel_exact()/trace_exact(), restructured so that a chain advances by
+// exactly ONE HitSpheres sweep per step() call: with one thread per chain all lanes of a warp then meet at a single
+// sweep call site every iteration (path rays and shadow rays alike) instead of diverging between the two call sites
+// of the nested-loop form. Used when many (frame,row) chains are batched (tpt_exact.cu, LANES = 1).
+namespace tpt {
+
+struct XChain
+{
+    uint32_t rng;
+    int x, s;                 // current pixel, sample index inside the pixel
+    V3 pix;                   // sum over the pixel's samples so far (Test.cpp:283-289)
+    V3 o, d;                  // ray of the next sweep
+    int kind;                 // 0: path ray, 1+j: shadow ray towards light j
+    int depth, n;             // Trace() recursion depth, number of stacked vertices
+    bool doMaterialE;
+    // the Lambert vertex whose lights are being sampled (Test.cpp:86-133)
+    V3 pos, normal, rdir, albedo, outDir, lightE, matE, contrib;
+    int mid, lightId;
+    V3 e[TPT_MAX_DEPTH + 1], a[TPT_MAX_DEPTH + 1];
+};
+
+// Test.cpp:286-288: next camera ray of the chain
+TPT_HD void xchain_begin_sample(XChain& c, const Camera88& cam, int y, float invWidth, float invHeight)
+{
+    float u = ((float)c.x + RandomFloat01(c.rng)) * invWidth;
+    float v = ((float)(uint32_t)y + RandomFloat01(c.rng)) * invHeight;
+    Ray r = GetRay<true>(cam, u, v, c.rng);
+    c.o = r.orig; c.d = r.dir;
+    c.kind = 0; c.depth = 0; c.n = 0; c.doMaterialE = true;
+}
+
+TPT_HD void xchain_begin(XChain& c, const Camera88& cam, int y, int frame, float invWidth, float invHeight)
+{
+    c.rng = row_seed(y, frame);
+    c.x = 0; c.s = 0; c.pix = v3(0, 0, 0);
+    xchain_begin_sample(c, cam, y, invWidth, invHeight);
+}
+
+// One sweep + the scatter logic that follows it. Returns true when pixel c.x has been completed: `pixelOut` then holds
+// col * (1/spp) of that pixel (before the blend) and c.x has advanced; the caller stores it and stops at c.x == width.
+template <class Hitter>
+TPT_HD bool xchain_step(const SceneView& sc, const Camera88& cam, XChain& c, int y, int spp, int width, float invWidth,
+                        float invHeight, unsigned& rayCount, const Hitter& hitter, V3& pixelOut)
+{
+    ++rayCount;
+    float t;
+    const int id = hitter.hit(sc, c.o, c.d, TPT_MIN_T, TPT_MAX_T, t);
+    bool haveResult = false, nextLight = false;
+    V3 result = v3(0, 0, 0);
+    int j = 0;
+    if (c.kind == 0)
+    {
+        if (id < 0) { result = sky(c.d); haveResult = true; }
+        else
+        {
+            Q4 s = ld_sph(sc, id);
+            V3 pos = c.o + c.d * t;
+            V3 normal = (pos - v3(s.x, s.y, s.z)) * sc.invRadius[id];
+            const int mid = id < sc.count ? id : sc.count;
+            Mat mat = load_mat(sc, mid);
+            V3 matE = mat.emissive;
+            if (c.depth >= TPT_MAX_DEPTH) { result = matE; haveResult = true; }
+            else if (mat.type == kLambert)
+            {
+                V3 target = pos + normal + RandomUnitVector<true>(c.rng);
+                c.outDir = M<true>::normalize(target - pos);
+                c.albedo = mat.albedo;
+                c.lightE = v3(0, 0, 0);
+                c.pos = pos; c.normal = normal; c.rdir = c.d; c.matE = matE; c.mid = mid;
+                nextLight = true; j = 0;
+            }
+            else
+            {
+                V3 attenuation, outDir;
+                if (!scatter_specular<true>(mat, c.d, pos, normal, c.rng, attenuation, outDir)) { result = matE; haveResult = true; }
+                else
+                {
+                    if (!c.doMaterialE) matE = v3(0, 0, 0);
+                    c.doMaterialE = true;                       // mat.type != Lambert (Test.cpp:214)
+                    c.e[c.n] = matE + v3(0, 0, 0);              // matE + lightE with Scatter's outLightE = 0 (Test.cpp:85)
+                    c.a[c.n] = attenuation;
+                    ++c.n;
+                    c.o = pos; c.d = outDir; ++c.depth;
+                }
+            }
+        }
+    }
+    else
+    {
+        if (id == c.lightId) c.lightE = c.lightE + c.contrib;
+        nextLight = true; j = c.kind;                           // kind = 1 + (light just traced)
+    }
+    if (nextLight)
+    {
+        while (j < sc.nLights && sc.lights[j].id == c.mid) ++j; // Test.cpp:100
+        if (j < sc.nLights)
+        {
+            const LightRec L = sc.lights[j];
+            V3 l;
+            sample_light<true>(L, c.pos, c.normal, c.rdir, c.albedo, c.rng, l, c.contrib);
+            c.o = c.pos; c.d = l; c.kind = 1 + j; c.lightId = L.id;
+        }
+        else
+        {
+            V3 matE = c.matE;
+            if (!c.doMaterialE) matE = v3(0, 0, 0);             // Test.cpp:210
+            c.doMaterialE = false;                              // Test.cpp:214 (Lambert)
+            c.e[c.n] = matE + c.lightE;
+            c.a[c.n] = c.albedo;
+            ++c.n;
+            c.o = c.pos; c.d = c.outDir; ++c.depth; c.kind = 0;
+        }
+    }
+    if (!haveResult) return false;
+    for (int k = c.n - 1; k >= 0; --k) result = c.e[k] + c.a[k] * result;   // Test.cpp:216, back to front
+    c.pix = c.pix + result;
+    bool pixelDone = false;
+    if (++c.s == spp)
+    {
+        pixelOut = c.pix * M<true>::div_(1.0f, (float)spp);
+        c.pix = v3(0, 0, 0); c.s = 0; ++c.x;
+        pixelDone = true;
+    }
+    if (c.x < width) xchain_begin_sample(c, cam, y, invWidth, invHeight);
+    return pixelDone;
+}
+
+} // namespace tpt
