@@ -71,6 +71,7 @@ __global__ void k_trace_exact(DrawParams p, const unsigned char* __restrict__ bl
 
 // One thread per chain, flat form: every loop iteration is one xchain_step() = one sphere sweep, so the lanes of a
 // warp (the same row in 32 consecutive frames) stay converged on the sweep whatever their paths are doing.
+template <int LANES>
 __global__ void __launch_bounds__(128)
 k_trace_exact_flat(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights, uint32_t stagedBytes)
 {
@@ -78,7 +79,9 @@ k_trace_exact_flat(DrawParams p, const unsigned char* __restrict__ blob, SceneBl
     __shared__ uint64_t bar;
     stage_blob(smem, blob, stagedBytes, &bar);
     SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
-    const long long chain = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int sub = threadIdx.x % LANES;
+    const long long chain = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
     const long long totalChains = (long long)p.numRows * p.numFrames;
     if (chain >= totalChains) return;
     const int ri = (int)(chain / p.numFrames);
@@ -88,7 +91,9 @@ k_trace_exact_flat(DrawParams p, const unsigned char* __restrict__ blob, SceneBl
     const float lerpFac = lerp_fac(frame, p.flags);
     const float oneMinus = 1.0f - lerpFac;
     const size_t imgRow = (size_t)(p.packed ? ri : y) * p.width;
-    SerialHitter<true> hitter;
+    GroupHitter<true, LANES> hitter;       // LANES lanes share the chain: replicated state, split sweep (see k_trace_exact)
+    hitter.sub = sub;
+    hitter.mask = LANES == 32 ? 0xffffffffu : (((1u << (LANES & 31)) - 1u) << (lane - sub));
     unsigned rc = 0;
     XChain c;
     xchain_begin(c, p.cam, y, frame, p.invWidth, p.invHeight);
@@ -96,7 +101,7 @@ k_trace_exact_flat(DrawParams p, const unsigned char* __restrict__ blob, SceneBl
     {
         const int x = c.x;
         V3 col;
-        if (xchain_step(sc, p.cam, c, y, p.spp, p.width, p.invWidth, p.invHeight, rc, hitter, col))
+        if (xchain_step(sc, p.cam, c, y, p.spp, p.width, p.invWidth, p.invHeight, rc, hitter, col) && sub == 0)
         {
             if (p.numFrames == 1)
             {
@@ -114,7 +119,18 @@ k_trace_exact_flat(DrawParams p, const unsigned char* __restrict__ blob, SceneBl
             }
         }
     }
-    atomicAdd(p.rayCounter + fi, (unsigned long long)rc);
+    if (sub == 0) atomicAdd(p.rayCounter + fi, (unsigned long long)rc);
+}
+
+template <int LANES>
+static cudaError_t launch_exact_flat_t(const DrawParams& p, const SceneDev& sc, cudaStream_t stream)
+{
+    const long long threads = (long long)p.numRows * p.numFrames * LANES;
+    auto kern = k_trace_exact_flat<LANES>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc.stagedBytes);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)((threads + 127) / 128), 128, sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes);
+    return cudaGetLastError();
 }
 
 // Sequential progressive blend of the per-frame colours (Test.cpp:272-276,293-295), one thread per pixel,
@@ -182,16 +198,10 @@ cudaError_t launch_exact(const DrawParams& p, const SceneDev& sc, int lanes, cud
     const int block = threads >= 148LL * 256 ? 128 : (threads >= 148LL * 64 ? 64 : 32);
     switch (lanes)
     {
-    case 1:
-    {
-        e = cudaFuncSetAttribute(k_trace_exact_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc.stagedBytes);
-        if (e != cudaSuccess) return e;
-        k_trace_exact_flat<<<(unsigned)((totalChains + 127) / 128), 128, sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes);
-        e = cudaGetLastError();
-        break;
-    }
+    case 1: e = launch_exact_flat_t<1>(p, sc, stream); break;
     case 2: e = launch_exact_t<1>(p, sc, stream, block); break;      // nested-loop form, one lane per chain (kept for comparison)
-    case 8: e = launch_exact_t<8>(p, sc, stream, block); break;
+    case 8: e = launch_exact_flat_t<8>(p, sc, stream); break;
+    case 9: e = launch_exact_t<8>(p, sc, stream, block); break;      // nested-loop form, 8 lanes per chain (comparison)
     case 32: e = launch_exact_t<32>(p, sc, stream, block); break;
     default: return cudaErrorInvalidValue;
     }
