@@ -52,8 +52,8 @@ int tpt_set_camera(tpt_context* ctx, const void* camera88);
 /* DO_SAMPLES_PER_PIXEL (Config.h:22), default 4. */
 int tpt_set_spp(tpt_context* ctx, int spp);
 /* Implementation knobs (benchmarks/tests): "fast_variant" (0 megakernel, 1/2 persistent tiles, 3/4 persistent queue; default 3), "exact_lanes"
- * (0 auto; 32 or 8 lanes per (frame,row) chain; 1 = one thread per chain; 8 and 1 run the flat one-sweep-per-step state
- * machine, 9 and 2 are the same widths as nested loops, for comparison), "register_host" (1: page-lock the caller's host backbuffer with cudaHostRegister the first
+ * (0 auto; 32 or 8 lanes per (frame,row) chain as nested loops; 1 = one thread per chain as a flat one-sweep-per-step
+ * state machine; 2 = one thread per chain nested, 9 = 8 lanes flat: measured slower, kept for comparison), "register_host" (1: page-lock the caller's host backbuffer with cudaHostRegister the first
  * time it is seen so both copies run at full PCIe rate; only safe when the buffer outlives the context, as a
  * reference shell's does; default 0 — buffers that are already pinned are detected by CUDA on their own), "host_bands" (1..8, default 3:
  * host-buffer fast draws are split into row bands on separate streams so the D2H of one band overlaps the tracing of

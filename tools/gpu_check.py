@@ -39,7 +39,7 @@ for lanes in (32, 8, 1):
 
 # exact batched: 16 frames in one call vs reference progressive
 rbuf16, rrays16 = pyoracle.ref_render(w, h, 0, 16, flags=2)
-for lanes in (0, 1, 8, 32):
+for lanes in (0, 1, 2, 8, 9, 32):
     ctx.set_option("exact_lanes", lanes)
     buf = np.zeros((h, w, 4), np.float32)
     tot, pf = ctx.draw(0, 16, w, h, buf, flags=2, mode=tpt.MODE_EXACT, per_frame=True)
