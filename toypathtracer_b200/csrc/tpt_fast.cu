@@ -377,8 +377,8 @@ struct FastHitterK
     int simdCount;
     __device__ __forceinline__ float4 ld(int i) const
     {
-        float4 r;
-        asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(sphK + (uint32_t)i * 16u));
+        float4 r;   // volatile: must not be hoisted above the barrier that follows the in-place {s, r^2} -> {s, K} rewrite
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(sphK + (uint32_t)i * 16u));
         return r;
     }
     __device__ __forceinline__ int hit(const SceneView&, V3 o, V3 d, float tMin, float tMax, float& tOut) const
@@ -434,14 +434,16 @@ struct FastHitterK
     }
 };
 
-// Builds {s, K} for every staged sphere (one CTA-wide pass, double precision for the cancellation |s|^2 - r^2).
-__device__ __forceinline__ void build_sphK(const SceneView& sc, float4* dst)
+// Rewrites the staged sphere array IN PLACE from {s, r^2} to {s, K} (one CTA-wide pass, double precision for the
+// cancellation |s|^2 - r^2). The fast kernels need r^2 nowhere else (the normal uses the centre and invRadius), so the
+// expanded form costs no extra shared memory and works for any sphere count.
+__device__ __forceinline__ void build_sphK(const SceneView& sc, float4* sphInSmem)
 {
     for (int i = threadIdx.x; i < sc.simdCount; i += blockDim.x)
     {
-        const Q4 s = ld_sph(sc, i);
+        const float4 s = sphInSmem[i];
         const double K = (double)s.x * s.x + (double)s.y * s.y + (double)s.z * s.z - (double)s.w;
-        dst[i] = make_float4(s.x, s.y, s.z, i < sc.count ? (float)K : 1.0e30f);
+        sphInSmem[i].w = i < sc.count ? (float)K : 1.0e30f;
     }
 }
 
@@ -582,10 +584,10 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
     stage_blob(smem, blob, stagedBytes, &bar);
     if (threadIdx.x == 0) { float wp; blend_weights(p, sW, wp); }
     SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
-    float4* sphK = reinterpret_cast<float4*>(smem + ((stagedBytes + 15u) & ~15u));
+    float4* sphK = reinterpret_cast<float4*>(smem + L.offSph);
     if (KFORM) build_sphK(sc, sphK);
     __syncthreads();
-    FastHitterK hitK; hitK.sphK = smem_u32(sphK); hitK.simdCount = sc.simdCount;
+    FastHitterK hitK; hitK.sphK = sc.sphShared; hitK.simdCount = sc.simdCount;
     SerialHitter<false> hitS;
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
@@ -722,9 +724,9 @@ k_fast_tileq(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
     if (threadIdx.x == 0) { float wp; blend_weights(p, sW, wp); }
     for (int i = threadIdx.x; i < kTileQPix * 3; i += kQueueThreads) sAcc[i] = 0.0f;
     SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
-    float4* sphK = reinterpret_cast<float4*>(smem + ((stagedBytes + 15u) & ~15u));
+    float4* sphK = reinterpret_cast<float4*>(smem + L.offSph);
     if (KFORM) build_sphK(sc, sphK);
-    FastHitterK hitK; hitK.sphK = smem_u32(sphK); hitK.simdCount = sc.simdCount;
+    FastHitterK hitK; hitK.sphK = sc.sphShared; hitK.simdCount = sc.simdCount;
     SerialHitter<false> hitS;
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
@@ -1204,11 +1206,10 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
     }
     if (variant == 3 || variant == 4)
     {
-        // expanded-form sweep (8 FP32 slots/test) needs 16 B/sphere more shared memory: small scenes only
-        const int simdCount = (sc.count + 3) / 4 * 4;
-        const bool kform = simdCount <= 512 && !g_disableKForm;
+        // expanded-form sweep (8 FP32 slots/test): K replaces r^2 in the staged sphere array
+        const bool kform = !g_disableKForm;
         auto kern = variant == 3 ? (kform ? k_fast_queue<6, true> : k_fast_queue<6, false>) : (kform ? k_fast_queue<8, true> : k_fast_queue<8, false>);
-        const size_t dyn3 = ((sc.stagedBytes + 15u) & ~15u) + (kform ? (size_t)simdCount * 16 : 0);
+        const size_t dyn3 = sc.stagedBytes;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn3);
         if (e != cudaSuccess) return e;
         int perSM = 0;
@@ -1279,10 +1280,9 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
     }
     if (variant == 5)
     {
-        const int simdCount = (sc.count + 3) / 4 * 4;
-        const bool kform = simdCount <= 512 && !g_disableKForm;
+        const bool kform = !g_disableKForm;
         auto kern = kform ? k_fast_tileq<6, true> : k_fast_tileq<6, false>;
-        const size_t dyn5 = ((sc.stagedBytes + 15u) & ~15u) + (kform ? (size_t)simdCount * 16 : 0);
+        const size_t dyn5 = sc.stagedBytes;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn5);
         if (e != cudaSuccess) return e;
         int perSM = 0;
