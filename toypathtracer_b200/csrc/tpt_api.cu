@@ -217,6 +217,13 @@ int tpt_set_scene(tpt_context* ctx, const void* spheres20, const void* materials
     ctx->scene.nLights = nLights;
     // small scenes: stage everything (spheres + materials); large ones: geometry only, materials from L2
     ctx->scene.stagedBytes = L.totalBytes <= 64 * 1024 ? L.totalBytes : L.geomBytes;
+    ctx->scene.kformOk = true;
+    for (int i = 0; i < count; ++i)
+    {
+        const Sphere20& s = ((const Sphere20*)spheres20)[i];
+        const double c2 = (double)s.center[0] * s.center[0] + (double)s.center[1] * s.center[1] + (double)s.center[2] * s.center[2];
+        if (c2 > 128.0 + 2.0 * (double)s.radius * s.radius) ctx->scene.kformOk = false;
+    }
     memcpy(&ctx->cam, camera88, sizeof(Camera88));
     ctx->haveScene = true;
     return 0;

@@ -377,8 +377,8 @@ struct FastHitterK
     int simdCount;
     __device__ __forceinline__ float4 ld(int i) const
     {
-        float4 r;   // volatile: must not be hoisted above the barrier that follows the in-place {s, r^2} -> {s, K} rewrite
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(sphK + (uint32_t)i * 16u));
+        float4 r;
+        asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(sphK + (uint32_t)i * 16u));
         return r;
     }
     __device__ __forceinline__ int hit(const SceneView&, V3 o, V3 d, float tMin, float tMax, float& tOut) const
@@ -588,6 +588,9 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
     if (KFORM) build_sphK(sc, sphK);
     __syncthreads();
     FastHitterK hitK; hitK.sphK = sc.sphShared; hitK.simdCount = sc.simdCount;
+    // the sweep's loads are plain (schedulable) asm: make their address opaque AFTER the barrier so that none of them can
+    // be hoisted above the in-place {s, r^2} -> {s, K} rewrite
+    asm volatile("" : "+r"(hitK.sphK));
     SerialHitter<false> hitS;
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
@@ -726,7 +729,9 @@ k_fast_tileq(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
     SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
     float4* sphK = reinterpret_cast<float4*>(smem + L.offSph);
     if (KFORM) build_sphK(sc, sphK);
+    __syncthreads();
     FastHitterK hitK; hitK.sphK = sc.sphShared; hitK.simdCount = sc.simdCount;
+    asm volatile("" : "+r"(hitK.sphK));     // see k_fast_queue
     SerialHitter<false> hitS;
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
@@ -1207,7 +1212,7 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
     if (variant == 3 || variant == 4)
     {
         // expanded-form sweep (8 FP32 slots/test): K replaces r^2 in the staged sphere array
-        const bool kform = !g_disableKForm;
+        const bool kform = !g_disableKForm && sc.kformOk;
         auto kern = variant == 3 ? (kform ? k_fast_queue<6, true> : k_fast_queue<6, false>) : (kform ? k_fast_queue<8, true> : k_fast_queue<8, false>);
         const size_t dyn3 = sc.stagedBytes;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn3);
@@ -1280,7 +1285,7 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
     }
     if (variant == 5)
     {
-        const bool kform = !g_disableKForm;
+        const bool kform = !g_disableKForm && sc.kformOk;
         auto kern = kform ? k_fast_tileq<6, true> : k_fast_tileq<6, false>;
         const size_t dyn5 = sc.stagedBytes;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn5);

@@ -11,6 +11,8 @@ struct SceneDev
     SceneBlobLayout layout;
     int count, nLights;
     uint32_t stagedBytes;        // prefix of the blob every CTA stages into shared memory via TMA
+    bool kformOk;                // every sphere satisfies |c|^2 <= 128 + 2 r^2: the expanded-form sweep of the fast kernels
+                                 // then rounds no worse than the reference form (see FastHitterK)
 };
 
 // lanes: 0 = choose from the number of (frame,row) chains; 1, 8 or 32 to force.
