@@ -346,6 +346,27 @@ __device__ __forceinline__ void red_add_f4(float* addr, float x, float y, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(0.0f) : "memory");
 }
 
+// Camera rays of one slab (<= kSlabPix consecutive pixels of the region, one sample index), generated by the whole warp
+// in one convergent burst (Test.cpp:286-288 + Maths.h:437-442) into the warp's shared buffer:
+// {origin.xyz, rng state} {direction.xyz, tag}; tag = image float4 offset (tileBase < 0) or tileBase + q.
+__device__ __forceinline__ void generate_slab_rays(const DrawParams& p, float4 (*rays)[2], int lane, uint32_t count,
+                                                   int x0, int ri0, uint32_t sample, uint32_t frame, int tileBase)
+{
+    for (uint32_t q = (uint32_t)lane; q < count; q += 32)
+    {
+        int x = x0 + (int)q, ri = ri0;
+        while (x >= p.width) { x -= p.width; ++ri; }
+        const int y = p.row0 + ri * p.rowStep;
+        uint32_t rng = pixel_seed((uint32_t)(y * p.width + x) * (uint32_t)p.spp + sample, frame);
+        float u = ((float)x + RandomFloat01(rng)) * p.invWidth;
+        float v = ((float)y + RandomFloat01(rng)) * p.invHeight;
+        Ray r = GetRay<false>(p.cam, u, v, rng);
+        const uint32_t tag = tileBase < 0 ? (uint32_t)((p.packed ? ri : y) * p.width + x) : (uint32_t)tileBase + q;
+        rays[q][0] = make_float4(r.orig.x, r.orig.y, r.orig.z, __uint_as_float(rng));
+        rays[q][1] = make_float4(r.dir.x, r.dir.y, r.dir.z, __uint_as_float(tag));
+    }
+}
+
 struct QPath
 {
     V3 o, d;
@@ -647,19 +668,7 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
                 slabW = invSpp * sW[fi];
                 slabBand = bandDone ? mtile / mtilesPerBand : 0u;
                 __syncwarp();       // every lane has popped what it needed from the previous slab
-                for (uint32_t q = (uint32_t)lane; q < slabEnd; q += 32)
-                {
-                    int x = slabX0 + (int)q, ri = slabRi0;
-                    while (x >= p.width) { x -= p.width; ++ri; }
-                    const int y = p.row0 + ri * p.rowStep;
-                    uint32_t rng = pixel_seed((uint32_t)(y * p.width + x) * (uint32_t)p.spp + slabSample, slabFrame);
-                    float u = ((float)x + RandomFloat01(rng)) * p.invWidth;
-                    float v = ((float)y + RandomFloat01(rng)) * p.invHeight;
-                    Ray r = GetRay<false>(p.cam, u, v, rng);
-                    sRays[threadIdx.x >> 5][q][0] = make_float4(r.orig.x, r.orig.y, r.orig.z, __uint_as_float(rng));
-                    sRays[threadIdx.x >> 5][q][1] = make_float4(r.dir.x, r.dir.y, r.dir.z,
-                                                                __uint_as_float((uint32_t)((p.packed ? ri : y) * p.width + x)));
-                }
+                generate_slab_rays(p, sRays[threadIdx.x >> 5], lane, slabEnd, slabX0, slabRi0, slabSample, slabFrame, -1);
                 __syncwarp();
             }
             const uint32_t avail = slabEnd - slabCur;
@@ -781,18 +790,7 @@ k_fast_tileq(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
                     slabFrame = (uint32_t)p.frame0 + fi;
                     slabW = invSpp * sW[fi];
                     __syncwarp();
-                    for (uint32_t q = (uint32_t)lane; q < slabEnd; q += 32)
-                    {
-                        int x = slabX0 + (int)q, ri = slabRi0;
-                        while (x >= p.width) { x -= p.width; ++ri; }
-                        const int y = p.row0 + ri * p.rowStep;
-                        uint32_t rng = pixel_seed((uint32_t)(y * p.width + x) * (uint32_t)p.spp + slabSample, slabFrame);
-                        float u = ((float)x + RandomFloat01(rng)) * p.invWidth;
-                        float v = ((float)y + RandomFloat01(rng)) * p.invHeight;
-                        Ray r = GetRay<false>(p.cam, u, v, rng);
-                        sRays[threadIdx.x >> 5][q][0] = make_float4(r.orig.x, r.orig.y, r.orig.z, __uint_as_float(rng));
-                        sRays[threadIdx.x >> 5][q][1] = make_float4(r.dir.x, r.dir.y, r.dir.z, __uint_as_float(slabQ0 + q));
-                    }
+                    generate_slab_rays(p, sRays[threadIdx.x >> 5], lane, slabEnd, slabX0, slabRi0, slabSample, slabFrame, (int)slabQ0);
                     __syncwarp();
                 }
                 const uint32_t avail = slabEnd - slabCur;
