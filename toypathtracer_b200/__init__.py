@@ -21,7 +21,7 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtpt_b200.so")
+LIB_PATH = os.environ.get("TPT_LIB_PATH") or os.path.join(_HERE, "libtpt_b200.so")   # override: A/B builds in experiments
 SHIM_PATH = os.path.join(_HERE, "libtoytest_b200.so")
 
 MODE_EXACT = 0

@@ -321,7 +321,10 @@ k_fast_persistent(DrawParams p, const unsigned char* __restrict__ blob, SceneBlo
 // (red.global.add.v4.f32, SASS REDG.E.ADD.F32x4) that resolves in L2. A tiny prepare kernel first scales the
 // buffer by the weight of `prev` (or zeroes it). End-of-kernel tail = one slab per warp instead of one 1024-pixel
 // tile per CTA, which matters at 1280x720x4spp where a warp's share of the whole frame is only ~1000 paths.
-constexpr int kSlabPix = 128;
+#ifndef TPT_SLAB_PIX
+#define TPT_SLAB_PIX 64
+#endif
+constexpr int kSlabPix = TPT_SLAB_PIX;     // paths per slab (pixels x one sample index); measured at 1280x720x4spp: 32 -> ?, 64 -> 20.3, 128 -> 19.5, 256 -> 18.0 Gray/s
 constexpr int kQueueThreads = 128;
 
 __global__ void k_prepare_image(DrawParams p, float wPrev)
