@@ -324,8 +324,12 @@ k_fast_persistent(DrawParams p, const unsigned char* __restrict__ blob, SceneBlo
 #ifndef TPT_SLAB_PIX
 #define TPT_SLAB_PIX 64
 #endif
-constexpr int kSlabPix = TPT_SLAB_PIX;     // paths per slab (pixels x one sample index); measured at 1280x720x4spp: 32 -> ?, 64 -> 20.3, 128 -> 19.5, 256 -> 18.0 Gray/s
-constexpr int kQueueThreads = 128;
+constexpr int kSlabPix = TPT_SLAB_PIX;     // paths per slab (pixels x one sample index); measured at 1280x720x4spp: 32 -> 20.1, 64 -> 20.3, 128 -> 19.5, 256 -> 18.0 Gray/s
+#ifndef TPT_QUEUE_THREADS
+#define TPT_QUEUE_THREADS 128
+#define TPT_QUEUE_MINB 6
+#endif
+constexpr int kQueueThreads = TPT_QUEUE_THREADS;   // measured at 1280x720x4spp: 64 -> 20.33, 128 -> 20.33, 256 -> 20.46 Gray/s
 
 __global__ void k_prepare_image(DrawParams p, float wPrev)
 {
@@ -1214,7 +1218,7 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
     {
         // expanded-form sweep (8 FP32 slots/test): K replaces r^2 in the staged sphere array
         const bool kform = !g_disableKForm && sc.kformOk;
-        auto kern = variant == 3 ? (kform ? k_fast_queue<6, true> : k_fast_queue<6, false>) : (kform ? k_fast_queue<8, true> : k_fast_queue<8, false>);
+        auto kern = variant == 3 ? (kform ? k_fast_queue<TPT_QUEUE_MINB, true> : k_fast_queue<TPT_QUEUE_MINB, false>) : (kform ? k_fast_queue<8, true> : k_fast_queue<8, false>);
         const size_t dyn3 = sc.stagedBytes;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn3);
         if (e != cudaSuccess) return e;
@@ -1232,7 +1236,7 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
         const long long slabs = ((regionPix + kSlabPix - 1) / kSlabPix) * S;
         if (slabs > 0x7fffffffLL) return cudaErrorInvalidValue;
         long long grid = (long long)numSMs * perSM;
-        const long long warpsNeeded = (slabs + 3) / 4;   // 4 warps per CTA
+        const long long warpsNeeded = (slabs + kQueueThreads / 32 - 1) / (kQueueThreads / 32);
         if (grid > warpsNeeded) grid = warpsNeeded;
         e = cudaMemsetAsync(p.workCounter, 0, sizeof(unsigned int), stream);
         if (e != cudaSuccess) return e;
