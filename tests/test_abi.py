@@ -62,3 +62,48 @@ def test_scene_blob_padding_rules(libs):
     sph, mats, cam, em = libs.stress_scene(320, 180, count=4096)
     assert len(sph) == 4096 and len(em) == 6 and sph.dtype.itemsize == 20 and mats.dtype.itemsize == 36
     assert np.isfinite(sph["center"]).all()
+
+
+def test_header_is_plain_c_and_links(libs, tmp_path):
+    """include/tpt_b200.h must be consumable from C (the cgo / JNI / N-API style binding INTEGRATION.md shows): compile a
+    C translation unit that takes the address of every declared function and link it against libtpt_b200.so."""
+    import subprocess
+    hdr = open(os.path.join(ROOT, "include", "tpt_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(tpt_[a-z0-9_]+)\s*\(", hdr)))
+    src = tmp_path / "use.c"
+    src.write_text('#include "tpt_b200.h"\n#include <stdio.h>\ntypedef void (*fn_t)(void);\nint main(void) {\n  fn_t f[] = {' +
+                   ", ".join(f"(fn_t){n}" for n in names) +
+                   '};\n  printf("%d %d\\n", (int)(sizeof f / sizeof f[0]), tpt_device_count());\n  return f[0] == 0;\n}\n')
+    exe = tmp_path / "use"
+    libdir = os.path.dirname(libs.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-ltpt_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert int(out[0]) == len(names) and int(out[1]) >= 0
+
+
+def test_host_code_is_sanitizer_clean(tmp_path, oracle):
+    """ASan + UBSan build of the host-side product sources that run on every draw (scene packing, integrator source on
+    the host, glibc restatement) and of the oracle restatement: one small render each, no reports."""
+    import subprocess
+    src = tmp_path / "san.cpp"
+    src.write_text('''
+#include "tests/host_sim/exact_sim.cpp"
+#include <cstdio>
+int main() {
+    tpt::Sphere20 s[5]; tpt::Material36 m[5];
+    for (int i = 0; i < 5; ++i) { s[i] = {{float(i) - 2.f, 0.f, -1.f}, 0.45f, 0.f}; m[i] = {i % 3, {0.7f, 0.6f, 0.5f}, {i == 1 ? 4.f : 0.f, 0.f, 0.f}, 0.1f, 1.5f}; }
+    tpt::Camera88 c = {{0, 1, 4}, {-2, -1, 1}, {4, 0, 0}, {0, 2, -0.5f}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, 0.02f};
+    std::vector<float> buf(48 * 27 * 4, 0.f); long long rays[2];
+    sim_render_exact(s, m, 5, &c, 48, 27, 0, 2, 2, 4, buf.data(), rays, 2);
+    sim_render_exact_flat(s, m, 5, &c, 48, 27, 0, 2, 2, 4, buf.data(), rays, 2);
+    std::printf("%lld %lld\\n", rays[0], rays[1]);
+    return 0;
+}
+''')
+    exe = tmp_path / "san"
+    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-mfma", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+                    "-I", ROOT, str(src), "-o", str(exe), "-lpthread", "-lm"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert len(r.stdout.split()) == 2
