@@ -921,12 +921,17 @@ k_fast_wave(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayou
 
     for (;;)
     {
-        // ---- chunk refill (one thread), visible after the barrier
-        if (tid == 0 && !sExhausted && sNextPath >= sEndPath)
+        // ---- list reset + chunk refill (thread 0 only, between the previous iteration's last barrier and this one)
+        if (tid == 0)
         {
-            const uint32_t base = atomicAdd(p.workCounter, (unsigned)kWaveChunk);
-            if (base >= wa.totalPaths) sExhausted = 1;
-            else { sNextPath = base; sEndPath = base + kWaveChunk < wa.totalPaths ? base + kWaveChunk : wa.totalPaths; }
+            sLightCount = 0;
+            for (int t = 0; t < WT_COUNT; ++t) sCount[t] = 0;
+            if (!sExhausted && sNextPath >= sEndPath)
+            {
+                const uint32_t base = atomicAdd(p.workCounter, (unsigned)kWaveChunk);
+                if (base >= wa.totalPaths) sExhausted = 1;
+                else { sNextPath = base; sEndPath = base + kWaveChunk < wa.totalPaths ? base + kWaveChunk : wa.totalPaths; }
+            }
         }
         __syncthreads();
 
@@ -1167,7 +1172,6 @@ k_fast_wave(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayou
             }
         }
         __syncthreads();
-        if (tid == 0) { sLightCount = 0; for (int t = 0; t < WT_COUNT; ++t) sCount[t] = 0; }
     }
 #undef WFLD
     for (int off = 16; off > 0; off >>= 1) rc += __shfl_xor_sync(0xffffffffu, rc, off);
