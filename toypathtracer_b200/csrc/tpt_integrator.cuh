@@ -331,15 +331,15 @@ template <bool EXACT, int LANES> struct GroupHitter
         float bestT = tMax;
         int bestId = -1;
         for (int i = sub; i < sc.simdCount; i += LANES) test_sphere<EXACT>(ld_sph(sc, i), i, o, d, tMin, bestT, bestId);
-#pragma unroll
-        for (int off = LANES / 2; off > 0; off >>= 1)
-        {
-            float ot = __shfl_xor_sync(mask, bestT, off);
-            int oid = __shfl_xor_sync(mask, bestId, off);
-            if (oid >= 0 && hit_better(ot, oid, bestT, bestId)) { bestT = ot; bestId = oid; }
-        }
-        tOut = bestT;
-        return bestId;
+        // Nearest hit over the LANES lanes under the total order (t, id & 3, id) with two hardware warp reductions
+        // (REDUX) instead of log2(LANES) shuffle rounds: every candidate t is a positive float (t > tMin > 0, or tMax for
+        // "no hit"), so its bit pattern orders like an unsigned integer; among the lanes that hold the minimum, the key
+        // (id & 3) << 28 | id picks the SSE lane rule's winner (Maths.cpp:126-152).
+        const unsigned tBits = __reduce_min_sync(mask, __float_as_uint(bestT));
+        const unsigned key = (__float_as_uint(bestT) == tBits && bestId >= 0) ? (((unsigned)bestId & 3u) << 28) | (unsigned)bestId : 0xffffffffu;
+        const unsigned win = __reduce_min_sync(mask, key);
+        tOut = __uint_as_float(tBits);
+        return win == 0xffffffffu ? -1 : (int)(win & 0x0fffffffu);
     }
 };
 template <bool EXACT> struct GroupHitter<EXACT, 1> : SerialHitter<EXACT> { unsigned mask; int sub; };
