@@ -189,9 +189,9 @@ cudaError_t launch_exact(const DrawParams& p, const SceneDev& sc, int lanes, cud
     const long long totalChains = (long long)p.numRows * p.numFrames;
     if (lanes <= 0)
     {
-        // measured on B200 (profiles/r01): 720 chains -> 32 lanes (338 vs 172 vs 62 Mray/s for 32/8/1),
-        // 11 520 chains -> 8 lanes (2.32 vs 1.80 vs 0.95 Gray/s), 184 320 chains -> 1 lane (3.8 Gray/s)
-        lanes = totalChains >= 100000 ? 1 : (totalChains >= 4000 ? 8 : 32);
+        // measured on B200 (profiles/r01, with the REDUX reduction): 720 chains -> 32 lanes (448 vs 177 vs 61 Mray/s for
+        // 32/8/1), 11 520 chains -> 32 lanes (2.61 vs 2.48 vs 0.98 Gray/s), 184 320 chains -> 1 lane, flat form (5.8 Gray/s)
+        lanes = totalChains >= 100000 ? 1 : (totalChains >= 20000 ? 8 : 32);
     }
     cudaError_t e;
     const long long threads = totalChains * lanes;
