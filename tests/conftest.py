@@ -50,7 +50,7 @@ def host_sim(tmp_path_factory):
     import ctypes
     out = tmp_path_factory.mktemp("host_sim")
     libs_ = {}
-    for name in ("libm_check", "exact_sim"):
+    for name in ("libm_check", "exact_sim", "fastdiv_check"):
         so = str(out / f"{name}.so")
         subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-o", so,
                         os.path.join(ROOT, "tests", "host_sim", f"{name}.cpp"), "-lpthread", "-lm"], check=True)

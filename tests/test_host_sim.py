@@ -51,3 +51,13 @@ def test_flat_state_machine_matches_golden_and_oracle(host_sim, oracle):
     obuf, orays, pads = oracle.orc_render(s2, m2, c2, 160, 90, 3, 2, flags=2)
     buf, rays = sim_render(host_sim, s2, m2, c2, 160, 90, 3, 2, 2, flat=True)
     assert rays == orays and not bits_differ(buf, obuf, pads).any()
+
+
+def test_fastdiv_matches_integer_division(host_sim):
+    """tpt_fastdiv.h (path index -> pixel/sample in the wavefront kernel): every divisor shape, n < 2^31."""
+    L = host_sim["fastdiv_check"]
+    L.check_fastdiv.restype = ctypes.c_longlong
+    divisors = [1, 2, 3, 4, 5, 7, 16, 64, 100, 255, 256, 257, 1000, 1280, 1920, 3840, 4096, 65535, 65536, 65537, 1 << 20, (1 << 20) + 7,
+                (1 << 30) - 1, 1 << 30, 0x7fffffff]
+    for d in divisors:
+        assert L.check_fastdiv(ctypes.c_uint32(d), ctypes.c_uint32(d * 2654435761 & 0xffffffff), ctypes.c_longlong(200000)) == 0, d

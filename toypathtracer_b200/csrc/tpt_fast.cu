@@ -14,6 +14,7 @@
 #include "tpt_integrator.cuh"
 #include "tpt_device_utils.cuh"
 #include "tpt_launch.h"
+#include "tpt_fastdiv.h"
 
 namespace tpt {
 
@@ -867,19 +868,6 @@ constexpr int kWaveChunk = 4096;       // paths taken from the global counter at
 enum { WF_O = 0, WF_D, WF_THR, WF_COL, WF_NEXT, WF_THRALB, WF_NL, WF_ALB, WF_PEND, WF_POS, WF_NRM };
 enum { WT_MISS = 0, WT_LAMBERT, WT_METAL, WT_DIEL, WT_SHADOW, WT_TERMINAL, WT_COUNT };
 constexpr int kKindFree = 255;
-
-struct FastDiv { uint32_t mul, shift, d; };   // n / d for n < 2^31
-__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv f) { return f.d == 1 ? n : (uint32_t)__umulhi(n, f.mul) >> f.shift; }
-static FastDiv make_fastdiv(uint32_t d)
-{
-    FastDiv f; f.d = d; f.mul = 0; f.shift = 0;
-    if (d <= 1) return f;
-    uint32_t l = 0; while ((1u << l) < d) ++l;                    // ceil(log2 d)
-    const uint64_t m = ((1ull << (32 + l)) + d - 1) / d;            // may need 33 bits
-    if (m >> 32) { const uint64_t m2 = ((1ull << (31 + l)) + d - 1) / d; f.mul = (uint32_t)m2; f.shift = l - 1; }  // exact for n < 2^31
-    else { f.mul = (uint32_t)m; f.shift = l; }
-    return f;
-}
 
 struct WaveArgs
 {
