@@ -43,7 +43,11 @@ const char* tpt_last_error(tpt_context* ctx);
 
 /* Takes exactly what GetSceneDesc() exports (Test.cpp:377-384): `count` 20 B spheres, `count` 36 B materials,
  * one 88 B camera, the emissive sphere ids (Test.cpp:321-338). emissives == NULL derives the list from the
- * materials the way UpdateTest does. invRadius is recomputed (Maths.h:359). Call after every UpdateTest(). */
+ * materials the way UpdateTest does; ids outside [0,count) or a negative count are refused. invRadius is recomputed
+ * (Maths.h:359). Call after every UpdateTest(). The call never blocks on the GPU: the packed scene goes through a
+ * pinned staging buffer into the one of two device copies that no draw in flight reads (the per-frame
+ * UpdateSubresource of Cpp/Windows/TestWin.cpp:261-283 as an async double-buffered upload); draws issued afterwards
+ * wait for it on the device. Bytes identical to the scene already resident are not uploaded again. */
 int tpt_set_scene(tpt_context* ctx, const void* spheres20, const void* materials36, int count,
                   const void* camera88, const int* emissives, int emissiveCount);
 /* Camera only (UpdateTest rebuilds it every frame from the aspect ratio, Test.cpp:341). */
@@ -58,7 +62,10 @@ int tpt_set_spp(tpt_context* ctx, int spp);
  * reference shell's does; default 0 — buffers that are already pinned are detected by CUDA on their own), "host_bands" (1..8, default 3:
  * host-buffer fast draws are split into row bands on separate streams so the D2H of one band overlaps the tracing of
  * the next), "host_progress" (default 1: with fast variant 3/4 a single kernel publishes per-band completion counters and the
- * copy stream waits on them with cuStreamWaitValue32, "progress_bands" bands, default 4; 0 falls back to host_bands). */
+ * copy stream waits on them with cuStreamWaitValue32, "progress_bands" bands, default 4; 0 falls back to host_bands),
+ * "fast_kform" (default 1: the fast kernels may use the expanded-form sphere sweep when the scene passes the gate in
+ * tpt_set_scene; per context), "fast_alpha_zero" (default 0; 1: fast-mode draws whose `prev` has zero weight write
+ * alpha = 0 instead of keeping the buffer's alpha — saves the read over NVLink when the buffer is a peer GPU's). */
 int tpt_set_option(tpt_context* ctx, const char* key, int value);
 
 /* Replaces DrawTest() (Test.cpp:344-367) for frames [frameCount, frameCount+numFrames) — numFrames*spp samples
@@ -73,7 +80,13 @@ int tpt_set_option(tpt_context* ctx, const char* key, int value);
  *   outRayCount       NULL or receives the number of rays (every HitWorld call: camera, bounce, shadow —
  *                     Test.cpp:122,199) of this call; 64-bit because 3840x2160x64 spp exceeds INT_MAX.
  *   outRaysPerFrame   NULL or numFrames entries (exact mode only; fast mode fills entry 0 with the total).
- *   cudaStream        a cudaStream_t (NULL = the context's own stream). */
+ *   cudaStream        a cudaStream_t (NULL = the context's own stream).
+ * numRows == 0 is an empty shard: nothing is traced or copied, the ray counts are 0.
+ * Alpha: never written in exact mode (Maths.h:38). Fast mode keeps it too, except for a HOST buffer drawn with zero
+ * `prev` weight (flags without kFlagProgressive, or frame 0): `prev` is then not uploaded and the rendered rows get
+ * alpha = 0 — what every reference shell's zero-initialised buffer holds (TestWin.cpp:73-74).
+ * Ordering: a context owns one scene and one set of counters; its draws execute in issue order even when they are
+ * enqueued on different streams (each draw waits on the previous draw's end event). Use one context per thread. */
 int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int height,
              int row0, int numRows, int rowStep, int packed,
              float* backbuffer, int bufferOnDevice, unsigned testFlags, int mode,

@@ -23,8 +23,12 @@ def _have_gpu():
 
 
 def pytest_collection_modifyitems(config, items):
-    # `-m gpu` on a machine without a device must fail loudly rather than skip silently
-    pass
+    """`-m gpu` on a machine without a usable device (or without the built CUDA library) must fail loudly rather than
+    deselect/skip its way to a green run: there is no CPU fallback to test."""
+    expr = (config.getoption("-m") or "").strip()
+    if expr == "gpu" and any(it.get_closest_marker("gpu") for it in items) and not _have_gpu():
+        pytest.exit("-m gpu was requested but toypathtracer_b200 finds no CUDA device / libtpt_b200.so "
+                    "(the product has no CPU path)", returncode=1)
 
 
 @pytest.fixture(scope="session")

@@ -22,9 +22,22 @@ struct tpt_context
     bool haveTiming = false;
     std::string lastError;
 
-    // scene
-    unsigned char* dBlob = nullptr;
-    size_t blobCap = 0;
+    // scene: two device blobs + two pinned staging buffers. tpt_set_scene never blocks the host: the new blob goes
+    // into the slot the draws in flight are NOT reading, on its own stream (the per-frame scene update of the
+    // reference's GPU shells, Cpp/Windows/TestWin.cpp:261-283, as an async double-buffered upload); draws wait on the
+    // slot's upload event, uploads wait on the slot's last-use event.
+    unsigned char* dBlobs[2] = {nullptr, nullptr};
+    size_t blobCap[2] = {0, 0};
+    unsigned char* hBlob[2] = {nullptr, nullptr};
+    size_t hBlobCap[2] = {0, 0};
+    int curBlob = 0;
+    cudaStream_t uploadStream = nullptr;
+    cudaEvent_t uploadDone[2] = {nullptr, nullptr};
+    cudaEvent_t blobLastUse[2] = {nullptr, nullptr};
+    std::vector<unsigned char> lastBlob;          // bytes of the blob currently on the device (skip identical uploads)
+    cudaEvent_t lastDraw = nullptr;               // end of the most recent draw: draws of one context are serialised in
+    cudaStream_t lastDrawStream = nullptr;        // issue order even when they are enqueued on different streams
+    bool haveLastDraw = false;
     SceneDev scene{};
     Camera88 cam{};
     bool haveScene = false;
@@ -32,6 +45,8 @@ struct tpt_context
 
     // options
     int fastVariant = 3;
+    int fastKForm = 1;        // expanded-form sweep allowed (still gated per scene by SceneDev::kformOk)
+    int fastAlphaZero = 0;    // 1: fast-mode draws whose `prev` has zero weight write alpha = 0 instead of preserving it
     int exactLanes = 0;
     int registerHost = 0;
     size_t maxScratchBytes = (size_t)8 << 30;
@@ -41,13 +56,15 @@ struct tpt_context
     float* dScratch = nullptr; size_t scratchCap = 0;  // exact mode per-frame colours
     unsigned long long* dRayCounters = nullptr; int rayCounterCap = 0;   // [numFrames]
     unsigned long long* dAccum = nullptr;              // [0] total since last read, [1] last draw total
-    unsigned int* dWork = nullptr;
+    unsigned int* dWork = nullptr;                     // ring of work-counter slots, one per draw (kWorkSlots x 32 uints)
+    unsigned workSlot = 0;
     unsigned long long* hPinned = nullptr; int hPinnedCap = 0;
     void* registeredPtr = nullptr; size_t registeredBytes = 0;
     int lastLaunches = 0;
 
     // host-buffer draws: row bands pipelined over several streams (kernel of band b+1 overlaps D2H of band b)
     static const int kMaxBands = 8;
+    static const int kWorkSlots = 32;
     int hostBands = 3;
     cudaStream_t bandStream[kMaxBands] = {};
     cudaEvent_t bandEvent[kMaxBands] = {};
@@ -137,7 +154,14 @@ int tpt_create(int device, tpt_context** out)
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->evStop);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->dAccum, 2 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(ctx->dAccum, 0, 2 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->dWork, 256);   // 4 uints per concurrent launch (tile/slab, front, back cursors)
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->dWork, tpt_context::kWorkSlots * 32 * sizeof(unsigned int));   // per draw: 8 bands x 4 uints
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->uploadStream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i)
+    {
+        e = cudaEventCreateWithFlags(&ctx->uploadDone[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->blobLastUse[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lastDraw, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->forkEvent, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->dBandDone, 64);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->tlKernelEnd);
@@ -159,7 +183,7 @@ int tpt_create(int device, tpt_context** out)
         e = cudaStreamCreateWithPriority(&ctx->bandStream[b], cudaStreamNonBlocking, pr);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->bandEvent[b], cudaEventDisableTiming);
     }
-    if (e != cudaSuccess) { delete ctx; return (int)e; }
+    if (e != cudaSuccess) { tpt_destroy(ctx); return (int)e; }
     *out = ctx;
     return 0;
 }
@@ -170,8 +194,19 @@ void tpt_destroy(tpt_context* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->registeredPtr) cudaHostUnregister(ctx->registeredPtr);
-    cudaFree(ctx->dBlob); cudaFree(ctx->dImage); cudaFree(ctx->dScratch); cudaFree(ctx->dRayCounters);
+    cudaFree(ctx->dImage); cudaFree(ctx->dScratch); cudaFree(ctx->dRayCounters);
     cudaFree(ctx->dAccum); cudaFree(ctx->dWork);
+    for (int i = 0; i < 2; ++i)
+    {
+        cudaFree(ctx->dBlobs[i]);
+        if (ctx->hBlob[i]) cudaFreeHost(ctx->hBlob[i]);
+        if (ctx->uploadDone[i]) cudaEventDestroy(ctx->uploadDone[i]);
+        if (ctx->blobLastUse[i]) cudaEventDestroy(ctx->blobLastUse[i]);
+    }
+    if (ctx->uploadStream) cudaStreamDestroy(ctx->uploadStream);
+    if (ctx->lastDraw) cudaEventDestroy(ctx->lastDraw);
+    if (ctx->tlKernelEnd) cudaEventDestroy(ctx->tlKernelEnd);
+    for (int b = 0; b < 16; ++b) if (ctx->tlBand[b]) cudaEventDestroy(ctx->tlBand[b]);
     if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
     for (int b = 0; b < tpt_context::kMaxBands; ++b)
     {
@@ -195,6 +230,13 @@ int tpt_set_scene(tpt_context* ctx, const void* spheres20, const void* materials
     if (!ctx) return (int)cudaErrorInvalidValue;
     if (!spheres20 || !materials36 || !camera88 || count <= 0) return fail_msg(ctx, "tpt_set_scene: bad arguments");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    // the caller's emissive list indexes spheres/materials (Test.cpp:96-100): refuse what would read out of bounds
+    if (emissives)
+    {
+        if (emissiveCount < 0 || emissiveCount > count) return fail_msg(ctx, "tpt_set_scene: emissiveCount out of range");
+        for (int i = 0; i < emissiveCount; ++i)
+            if (emissives[i] < 0 || emissives[i] >= count) return fail_msg(ctx, "tpt_set_scene: emissive id out of range");
+    }
     std::vector<unsigned char> blob;
     SceneBlobLayout L;
     int nLights = 0;
@@ -202,21 +244,49 @@ int tpt_set_scene(tpt_context* ctx, const void* spheres20, const void* materials
     // geometry + light table must fit in shared memory next to the kernels' static shared arrays
     const uint32_t kMaxStage = 200 * 1024;
     if (L.geomBytes > kMaxStage) return fail_msg(ctx, "tpt_set_scene: too many spheres for shared-memory staging");
-    if (blob.size() > ctx->blobCap)
+    // A reference shell calls UpdateTest + upload every frame although the scene only changes under kFlagAnimate
+    // (Test.cpp:304-308): identical bytes are not uploaded again.
+    const bool same = ctx->haveScene && ctx->scene.count == count && blob == ctx->lastBlob;
+    if (!same)
     {
-        cudaFree(ctx->dBlob); ctx->dBlob = nullptr; ctx->blobCap = 0;
-        CK(cudaMalloc(&ctx->dBlob, blob.size()), "cudaMalloc scene");
-        ctx->blobCap = blob.size();
+        const int slot = ctx->haveScene ? (ctx->curBlob ^ 1) : 0;
+        // the slot's previous contents may still be read by draws issued before the last upload (device side: the
+        // upload stream waits on the slot's last-use event) and its staging buffer by that upload's DMA (host side)
+        CK(cudaEventSynchronize(ctx->uploadDone[slot]), "sync staging slot");
+        if (blob.size() > ctx->blobCap[slot])
+        {
+            CK(cudaEventSynchronize(ctx->blobLastUse[slot]), "sync before scene realloc");
+            cudaFree(ctx->dBlobs[slot]); ctx->dBlobs[slot] = nullptr; ctx->blobCap[slot] = 0;
+            CK(cudaMalloc(&ctx->dBlobs[slot], blob.size()), "cudaMalloc scene");
+            ctx->blobCap[slot] = blob.size();
+        }
+        if (blob.size() > ctx->hBlobCap[slot])
+        {
+            if (ctx->hBlob[slot]) cudaFreeHost(ctx->hBlob[slot]);
+            ctx->hBlob[slot] = nullptr; ctx->hBlobCap[slot] = 0;
+            CK(cudaMallocHost(&ctx->hBlob[slot], blob.size()), "cudaMallocHost scene staging");
+            ctx->hBlobCap[slot] = blob.size();
+        }
+        memcpy(ctx->hBlob[slot], blob.data(), blob.size());
+        CK(cudaStreamWaitEvent(ctx->uploadStream, ctx->blobLastUse[slot], 0), "upload waits for the slot's readers");
+        CK(cudaMemcpyAsync(ctx->dBlobs[slot], ctx->hBlob[slot], blob.size(), cudaMemcpyHostToDevice, ctx->uploadStream), "scene upload");
+        CK(cudaEventRecord(ctx->uploadDone[slot], ctx->uploadStream), "upload event");
+        ctx->curBlob = slot;
+        ctx->lastBlob.swap(blob);
     }
-    // the upload must not race with kernels of a previous draw that still read the old blob
-    CK(cudaStreamSynchronize(ctx->stream), "sync before scene upload");
-    CK(cudaMemcpy(ctx->dBlob, blob.data(), blob.size(), cudaMemcpyHostToDevice), "scene upload");
-    ctx->scene.blob = ctx->dBlob;
+    ctx->scene.blob = ctx->dBlobs[ctx->curBlob];
     ctx->scene.layout = L;
     ctx->scene.count = count;
     ctx->scene.nLights = nLights;
     // small scenes: stage everything (spheres + materials); large ones: geometry only, materials from L2
     ctx->scene.stagedBytes = L.totalBytes <= 64 * 1024 ? L.totalBytes : L.geomBytes;
+    // Expanded-form sweep gate (FastHitterK, tpt_fast.cu). With u = 2^-24 the expanded form evaluates
+    // c = |s-o|^2 - r^2 with |dc| <= ~4u (|s| + |o|)^2, the reference form (Maths.cpp:97-102) with |dc| <= ~4u |s-o|^2 + u r^2.
+    // The gate |s|^2 <= 128 + 2 r^2 keeps (|s| + |o|)^2 within a small multiple of max(r^2, 128) for origins inside the
+    // scene's extent (|o|^2 <= 128), i.e. the expanded form is no worse than ~8x the reference form's own bound for small
+    // spheres and BETTER than it for huge ones (ground sphere r = 100: 2 s.o ~ 400 vs |co|^2 ~ 10^4). The bound is not
+    // what the parity claim rests on: tests/test_gpu_fast.py compares kform 0 and 1 against the bit-exact mode at
+    // >= 16k spp, overall and per first-hit material.
     ctx->scene.kformOk = true;
     for (int i = 0; i < count; ++i)
     {
@@ -250,12 +320,24 @@ int tpt_set_option(tpt_context* ctx, const char* key, int value)
     if (!strcmp(key, "fast_variant")) { if (value < 0 || value > 7) return fail_msg(ctx, "fast_variant: 0..7"); ctx->fastVariant = value; return 0; }
     if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 8 && value != 9 && value != 32) return fail_msg(ctx, "exact_lanes: 0,1,2,8,9,32"); ctx->exactLanes = value; return 0; }
     if (!strcmp(key, "register_host")) { ctx->registerHost = value ? 1 : 0; return 0; }
-    if (!strcmp(key, "fast_kform")) { fast_set_kform(value != 0); return 0; }
+    if (!strcmp(key, "fast_kform")) { ctx->fastKForm = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "fast_alpha_zero")) { ctx->fastAlphaZero = value ? 1 : 0; return 0; }
     if (!strcmp(key, "host_progress")) { ctx->hostProgress = value ? 1 : 0; return 0; }
     if (!strcmp(key, "progress_bands")) { if (value < 1 || value > 16) return fail_msg(ctx, "progress_bands: 1..16"); ctx->progressBands = value; return 0; }
     if (!strcmp(key, "host_bands")) { if (value < 1 || value > tpt_context::kMaxBands) return fail_msg(ctx, "host_bands: 1..8"); ctx->hostBands = value; return 0; }
     if (!strcmp(key, "max_scratch_mb")) { if (value < 16) return fail_msg(ctx, "max_scratch_mb: >= 16"); ctx->maxScratchBytes = (size_t)value << 20; return 0; }
     return fail_msg(ctx, "tpt_set_option: unknown key");
+}
+
+// Copies the rows y_i = row0 + i*rowStep (or the packed band) of a float4 image between host and device.
+static cudaError_t copy_rows(float* dst, const float* src, int width, int row0, int numRows, int rowStep, int packed,
+                             cudaMemcpyKind kind, cudaStream_t stream)
+{
+    const size_t rowBytes = (size_t)width * 16;
+    if (packed) return cudaMemcpyAsync(dst, src, rowBytes * numRows, kind, stream);
+    const size_t off = (size_t)row0 * width * 4;
+    if (rowStep == 1) return cudaMemcpyAsync(dst + off, src + off, rowBytes * numRows, kind, stream);
+    return cudaMemcpy2DAsync(dst + off, rowBytes * rowStep, src + off, rowBytes * rowStep, rowBytes, numRows, kind, stream);
 }
 
 static int ensure(tpt_context* ctx, void** p, size_t* cap, size_t bytes, const char* what)
@@ -275,16 +357,31 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
 {
     if (!ctx) return (int)cudaErrorInvalidValue;
     if (!ctx->haveScene) return fail_msg(ctx, "tpt_draw: no scene (call tpt_set_scene after UpdateTest)");
-    if (!backbuffer || width <= 0 || height <= 0 || numFrames <= 0 || frameCount < 0 || numRows <= 0 || rowStep <= 0 || row0 < 0)
+    if (!backbuffer || width <= 0 || height <= 0 || numFrames <= 0 || frameCount < 0 || numRows < 0 || rowStep <= 0 || row0 < 0)
         return fail_msg(ctx, "tpt_draw: bad arguments");
-    if (row0 + (long long)(numRows - 1) * rowStep >= height) return fail_msg(ctx, "tpt_draw: rows outside the image");
     if (mode != TPT_MODE_EXACT && mode != TPT_MODE_FAST) return fail_msg(ctx, "tpt_draw: unknown mode");
+    if (numRows == 0)
+    {
+        // an empty shard (more ranks than rows, TraceRowJob(start, start)): nothing to trace, nothing to copy
+        if (outRayCount) *outRayCount = 0;
+        if (outRaysPerFrame) for (int i = 0; i < numFrames; ++i) outRaysPerFrame[i] = 0;
+        ctx->lastLaunches = 0;
+        return 0;
+    }
+    if (row0 + (long long)(numRows - 1) * rowStep >= height) return fail_msg(ctx, "tpt_draw: rows outside the image");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     cudaStream_t stream = cudaStreamArg ? (cudaStream_t)cudaStreamArg : ctx->stream;
+    // One context = one scene blob, one set of counters: draws are ordered in issue order even across streams, and the
+    // scene this draw reads must have landed (tpt_set_scene uploads asynchronously on its own stream).
+    if (ctx->haveLastDraw && ctx->lastDrawStream != stream) CK(cudaStreamWaitEvent(stream, ctx->lastDraw, 0), "order after previous draw");
+    CK(cudaStreamWaitEvent(stream, ctx->uploadDone[ctx->curBlob], 0), "wait for scene upload");
+    SceneDev scene = ctx->scene;
+    scene.kformOk = scene.kformOk && ctx->fastKForm;
 
     const size_t bufRows = packed ? (size_t)numRows : (size_t)height;
     const size_t bufBytes = bufRows * width * 4 * sizeof(float);
     float* dImage = backbuffer;
+    bool needPrev = true;
     if (!bufferOnDevice)
     {
         int r = ensure(ctx, (void**)&ctx->dImage, &ctx->imageCap, bufBytes, "cudaMalloc image");
@@ -304,7 +401,7 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
         // untouched alpha are part of bit parity). Fast mode uploads it only when prev has a non-zero weight;
         // otherwise the kernel writes alpha = 0, which is what every reference shell's zero-initialised buffer
         // holds (TestWin.cpp:73-74, Renderer.mm:148-149, Emscripten/main.cpp:50-51).
-        bool needPrev = mode == TPT_MODE_EXACT;
+        needPrev = mode == TPT_MODE_EXACT;
         if (!needPrev)
         {
             float wPrev = 1.0f;
@@ -312,7 +409,10 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
             needPrev = wPrev != 0.0f;
         }
         if (needPrev)
-            CK(cudaMemcpyAsync(dImage, backbuffer, bufBytes, cudaMemcpyHostToDevice, stream), "H2D backbuffer");
+        {
+            cudaError_t e = copy_rows(dImage, backbuffer, width, row0, numRows, rowStep, packed, cudaMemcpyHostToDevice, stream);
+            if (e != cudaSuccess) return fail(ctx, e, "H2D backbuffer");
+        }
     }
 
     // frames per launch: exact mode needs numFrames*numRows*width float4 of scratch when numFrames > 1
@@ -345,7 +445,10 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
     p.invWidth = 1.0f / (float)width;     // Test.cpp:270-271
     p.invHeight = 1.0f / (float)height;
     p.image = dImage;
-    p.workCounter = ctx->dWork;
+    p.workCounter = ctx->dWork + (size_t)(ctx->workSlot++ % tpt_context::kWorkSlots) * 32;
+    // alpha is never written by the reference (Maths.h:38). When `prev` has zero weight the fast kernels keep the alpha
+    // that is in the buffer, unless the staging image was not uploaded (host buffer) or the caller waived it.
+    p.zeroAlpha = (ctx->fastAlphaZero || (!bufferOnDevice && !needPrev)) ? 1 : 0;
 
     ctx->lastLaunches = 0;
     CK(cudaEventRecord(ctx->evStart, stream), "event record");
@@ -354,7 +457,9 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
     // overlaps the tracing of band b+1 and the persistent CTAs of band b+1 fill the SMs as band b's tail drains.
     bool pipelined = mode == TPT_MODE_FAST && !bufferOnDevice && ctx->fastVariant >= 3 && ctx->fastVariant <= 7 && ctx->hostBands > 1 &&
                      (rowStep == 1 || packed) && framesPerLaunch == numFrames && numRows >= 16 * ctx->hostBands;
-    const bool progress = pipelined && ctx->waitValue32 && ctx->hostProgress && (ctx->fastVariant == 3 || ctx->fastVariant == 4);
+    // the per-band completion counters are 32-bit (cuStreamWaitValue32): a band never holds more paths than the image
+    const bool progress = pipelined && ctx->waitValue32 && ctx->hostProgress && (ctx->fastVariant == 3 || ctx->fastVariant == 4) &&
+                          (long long)numRows * width * ctx->spp * numFrames <= 0xFFFFFFFFLL;
     if (progress)
     {
         // ONE kernel for the whole image; the copy stream waits on the kernel's per-band completion counters
@@ -364,7 +469,7 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
         CK(cudaEventRecord(ctx->forkEvent, stream), "fork event");
         CK(cudaStreamWaitEvent(ctx->copyStream, ctx->forkEvent, 0), "copy stream wait");
         p.frame0 = frameCount; p.numFrames = numFrames; p.rayCounter = ctx->dRayCounters;
-        cudaError_t e = launch_fast(p, ctx->scene, ctx->fastVariant, ctx->numSMs, stream, ctx->dBandDone, NB, expected);
+        cudaError_t e = launch_fast(p, scene, ctx->fastVariant, ctx->numSMs, stream, ctx->dBandDone, NB, expected);
         if (e != cudaSuccess) return fail(ctx, e, "kernel launch");
         ctx->lastLaunches += fast_kernel_launches(p, ctx->fastVariant);
         CK(cudaEventRecord(ctx->tlKernelEnd, stream), "timeline event");
@@ -398,10 +503,10 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
             DrawParams pb = p;
             pb.row0 = row0 + rb0 * rowStep;
             pb.numRows = rb1 - rb0;
-            pb.workCounter = ctx->dWork + 4 * b;
+            pb.workCounter = p.workCounter + 4 * b;
             const size_t firstRow = packed ? (size_t)rb0 : (size_t)(row0 + rb0);   // rowStep == 1 when not packed
             if (packed) pb.image = dImage + firstRow * width * 4;
-            cudaError_t e = launch_fast(pb, ctx->scene, ctx->fastVariant, ctx->numSMs, bs);
+            cudaError_t e = launch_fast(pb, scene, ctx->fastVariant, ctx->numSMs, bs);
             if (e != cudaSuccess) return fail(ctx, e, "kernel launch");
             ctx->lastLaunches += fast_kernel_launches(pb, ctx->fastVariant);
             const size_t off = firstRow * width * 4, bytes = (size_t)(rb1 - rb0) * width * 16;
@@ -426,13 +531,13 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
                 if (r) return r;
                 p.scratch = ctx->dScratch;
             }
-            e = launch_exact(p, ctx->scene, ctx->exactLanes, stream);
+            e = launch_exact(p, scene, ctx->exactLanes, stream);
             ctx->lastLaunches += nf > 1 ? 2 : 1;
         }
         else
         {
             p.rayCounter = ctx->dRayCounters;
-            e = launch_fast(p, ctx->scene, ctx->fastVariant, ctx->numSMs, stream);
+            e = launch_fast(p, scene, ctx->fastVariant, ctx->numSMs, stream);
             ctx->lastLaunches += fast_kernel_launches(p, ctx->fastVariant);
         }
         if (e != cudaSuccess) return fail(ctx, e, "kernel launch");
@@ -444,7 +549,15 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
     ctx->lastLaunches += 1;
 
     if (!bufferOnDevice && !pipelined)
-        CK(cudaMemcpyAsync(backbuffer, dImage, bufBytes, cudaMemcpyDeviceToHost, stream), "D2H backbuffer");
+    {
+        // only the rows this draw rendered go back: the caller's other rows are not ours to touch (TraceRowJob writes
+        // rows [start,end) only, Test.cpp:278-297)
+        cudaError_t e = copy_rows(backbuffer, dImage, width, row0, numRows, rowStep, packed, cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) return fail(ctx, e, "D2H backbuffer");
+    }
+    CK(cudaEventRecord(ctx->lastDraw, stream), "draw end event");
+    CK(cudaEventRecord(ctx->blobLastUse[ctx->curBlob], stream), "scene last-use event");
+    ctx->lastDrawStream = stream; ctx->haveLastDraw = true;
 
     if (outRayCount || outRaysPerFrame)
     {

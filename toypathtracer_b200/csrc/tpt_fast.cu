@@ -46,6 +46,20 @@ __device__ __forceinline__ void blend_weights(const DrawParams& p, float* w, flo
     wPrev = suffix;
 }
 
+// prev*wPrev + acc for one pixel (Test.cpp:293-295 with the frames of this draw folded into acc). A zero weight must
+// not read `prev` as a number (NaN * 0), but the pixel's alpha is still the buffer's: the reference never writes it
+// (Maths.h:38).
+__device__ __forceinline__ float4 blend_prev(const DrawParams& p, const float* px, float wPrev, float ax, float ay, float az)
+{
+    if (wPrev != 0.0f)
+    {
+        float4 prev = ld_stream_f4(px);
+        prev.x = prev.x * wPrev + ax; prev.y = prev.y * wPrev + ay; prev.z = prev.z * wPrev + az;
+        return prev;
+    }
+    return make_float4(ax, ay, az, p.zeroAlpha ? 0.0f : __ldg(px + 3));
+}
+
 // ---- variant 0 ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFastThreads)
 k_fast_mega(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights, uint32_t stagedBytes)
@@ -86,11 +100,7 @@ k_fast_mega(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayou
             acc = acc + col * (invSpp * sW[fi]);
         }
         float* px = p.image + ((size_t)(p.packed ? ri : y) * p.width + x) * 4;
-        float4 prev = make_float4(0, 0, 0, 0);
-        const float wPrev = sWPrev;
-        if (wPrev != 0.0f) prev = ld_stream_f4(px);
-        prev.x = prev.x * wPrev + acc.x; prev.y = prev.y * wPrev + acc.y; prev.z = prev.z * wPrev + acc.z;
-        st_stream_f4(px, prev);
+        st_stream_f4(px, blend_prev(p, px, sWPrev, acc.x, acc.y, acc.z));
     }
     // one atomic per warp
     for (int off = 16; off > 0; off >>= 1) rc += __shfl_xor_sync(0xffffffffu, rc, off);
@@ -300,12 +310,7 @@ k_fast_persistent(DrawParams p, const unsigned char* __restrict__ blob, SceneBlo
             const int ri = (int)(gp / p.width), x = (int)(gp % p.width);
             const int y = p.row0 + ri * p.rowStep;
             float* px = p.image + ((size_t)(p.packed ? ri : y) * p.width + x) * 4;
-            float4 prev = make_float4(0, 0, 0, 0);
-            if (wPrev != 0.0f) prev = ld_stream_f4(px);
-            prev.x = prev.x * wPrev + sAcc[i * 3 + 0];
-            prev.y = prev.y * wPrev + sAcc[i * 3 + 1];
-            prev.z = prev.z * wPrev + sAcc[i * 3 + 2];
-            st_stream_f4(px, prev);
+            st_stream_f4(px, blend_prev(p, px, wPrev, sAcc[i * 3 + 0], sAcc[i * 3 + 1], sAcc[i * 3 + 2]));
             sAcc[i * 3 + 0] = 0.0f; sAcc[i * 3 + 1] = 0.0f; sAcc[i * 3 + 2] = 0.0f;
         }
     }
@@ -340,12 +345,7 @@ __global__ void k_prepare_image(DrawParams p, float wPrev)
     const int ri = (int)(idx / p.width), x = (int)(idx % p.width);
     const int y = p.row0 + ri * p.rowStep;
     float* px = p.image + ((size_t)(p.packed ? ri : y) * p.width + x) * 4;
-    float4 v = make_float4(0, 0, 0, 0);
-    if (wPrev != 0.0f)
-    {
-        v = ld_stream_f4(px);
-        v.x *= wPrev; v.y *= wPrev; v.z *= wPrev;
-    }
+    float4 v = blend_prev(p, px, wPrev, 0.0f, 0.0f, 0.0f);
     *reinterpret_cast<float4*>(px) = v;   // stays in L2 for the reductions that follow
 }
 
@@ -836,12 +836,7 @@ k_fast_tileq(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
             const int ri = (int)(gp / (uint32_t)p.width), x = (int)(gp - (uint32_t)ri * (uint32_t)p.width);
             const int y = p.row0 + ri * p.rowStep;
             float* px = p.image + ((size_t)(p.packed ? ri : y) * p.width + x) * 4;
-            float4 prev = make_float4(0, 0, 0, 0);
-            if (wPrev != 0.0f) prev = ld_stream_f4(px);
-            prev.x = prev.x * wPrev + sAcc[i * 3 + 0];
-            prev.y = prev.y * wPrev + sAcc[i * 3 + 1];
-            prev.z = prev.z * wPrev + sAcc[i * 3 + 2];
-            st_stream_f4(px, prev);
+            st_stream_f4(px, blend_prev(p, px, wPrev, sAcc[i * 3 + 0], sAcc[i * 3 + 1], sAcc[i * 3 + 2]));
             sAcc[i * 3 + 0] = 0.0f; sAcc[i * 3 + 1] = 0.0f; sAcc[i * 3 + 2] = 0.0f;
         }
     }
@@ -1167,13 +1162,10 @@ k_fast_wave(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayou
 }
 
 int fast_slab_pixels() { return kSlabPix; }
-bool g_disableKForm = false;
-void fast_set_kform(bool enabled) { g_disableKForm = !enabled; }
 
 int fast_kernel_launches(const DrawParams&, int variant) { return (variant == 3 || variant == 4 || variant == 6 || variant == 7) ? 2 : 1; }
 
 
-extern bool g_disableKForm;
 
 cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, int numSMs, cudaStream_t stream,
                         unsigned int* bandDone, int numBands, unsigned int* bandExpected)
@@ -1209,7 +1201,7 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
     if (variant == 3 || variant == 4)
     {
         // expanded-form sweep (8 FP32 slots/test): K replaces r^2 in the staged sphere array
-        const bool kform = !g_disableKForm && sc.kformOk;
+        const bool kform = sc.kformOk;
         auto kern = variant == 3 ? (kform ? k_fast_queue<TPT_QUEUE_MINB, true> : k_fast_queue<TPT_QUEUE_MINB, false>) : (kform ? k_fast_queue<8, true> : k_fast_queue<8, false>);
         const size_t dyn3 = sc.stagedBytes;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn3);
@@ -1282,7 +1274,7 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
     }
     if (variant == 5)
     {
-        const bool kform = !g_disableKForm && sc.kformOk;
+        const bool kform = sc.kformOk;
         auto kern = kform ? k_fast_tileq<6, true> : k_fast_tileq<6, false>;
         const size_t dyn5 = sc.stagedBytes;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn5);

@@ -26,6 +26,5 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
                         unsigned int* bandDone = nullptr, int numBands = 0, unsigned int* bandExpected = nullptr);
 int fast_slab_pixels();
 int fast_kernel_launches(const DrawParams& p, int variant);
-void fast_set_kform(bool enabled);   // expanded-form sphere sweep (default on for <= 512 spheres)
 
 } // namespace tpt

@@ -67,6 +67,7 @@ struct DrawParams
     int frame0, numFrames;    // frames [frame0, frame0+numFrames), N spp = N/spp reference frames
     int spp;                  // DO_SAMPLES_PER_PIXEL (Config.h:22)
     unsigned flags;           // kFlagAnimate = 1, kFlagProgressive = 2 (Test.h:4-8)
+    int zeroAlpha;            // fast mode, prev weight 0: 1 = write alpha 0, 0 = keep the buffer's alpha (Maths.h:38: never written)
     float invWidth, invHeight;
     float* image;             // full image base, width*height*4 floats, row 0 = bottom (device)
     float* scratch;           // exact mode, numFrames > 1: [numFrames][numRows][width] float4 per-frame colours
