@@ -13,10 +13,12 @@ call of the reference (UpdateTest + DrawTest): ~16.8 M rays (camera + bounce + s
   e2e     the same metric through the drop-in C-ABI with HOST buffers: per step tpt_set_scene (scene H2D, what
           UpdateTest+GetSceneDesc+UpdateSubresource do in the reference's GPU shells, TestWin.cpp:258-283) +
           tpt_draw (kernel, image D2H to pinned host memory, ray count D2H), wall clock around the synchronous call.
-  N > 1   frames are independent units (Test.cpp:280 seeds depend on the frame index): step s renders frames
-          s*N .. s*N+N-1, one per GPU (weak scaling: one frame per GPU per step); ONE all_reduce(sum) of the
-          14.7 MB image at the end of the timed region combines the ranks' frames (the exchange step of a
-          frame-sharded accumulation, multigpu.combine_frame_means). No collective inside the tracing.
+  N > 1   north_star's tiled image split, weak scaling: step s renders the N frames s*N .. s*N+N-1 of ONE 1280x720
+          image (accumulated with kFlagProgressive); rank r traces rows r, r+N, ... of all N frames (rows are the
+          independent RNG chains, Test.cpp:278-280) into its packed band, then ONE all_gather per step assembles the
+          14.7 MB image on every rank — inside the timed region. One frame's worth of rays per GPU per step at every N.
+          `strong` sub-record: BASELINE configs[3] (3840x2160, 64 spp, one image split over the N GPUs) with the 1-GPU
+          time of the same image, assembled A) by NCCL all_gather, B) by the tile kernel's peer stores over NVLink.
 
 --impl reference times the UNMODIFIED reference C++ path (oracle/_ref/libtoyref.so, enkiTS on all host threads)
 on the same workload; rank 0 only.
@@ -45,10 +47,13 @@ def load_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
     (per launch, same workload); None when no capture of this round's kernel is committed."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01", "ncu_traffic.json")))
-        return t.get("k_fast_queue_1280x720_4spp_dram_bytes")
+        for rnd in ("r02", "r01"):
+            path = os.path.join(ROOT, "profiles", rnd, "ncu_traffic.json")
+            if os.path.exists(path):
+                return json.load(open(path)).get("k_fast_queue_1280x720_4spp_dram_bytes")
     except Exception:
-        return None
+        pass
+    return None
 
 
 def load_peaks():
@@ -106,7 +111,7 @@ def run_reference(args, rank):
     if not pyoracle.have_ref():
         pyoracle.build()
     kind = "reference" if pyoracle.have_ref() else "port"
-    cores = os.cpu_count() or 1
+    cores, cpu_info = usable_cores()
     buf = np.zeros((H, W, 4), np.float32)
     if kind == "reference":
         render = lambda f0, n: pyoracle.ref_render(W, H, f0, n, flags=0, buf=buf, want_seconds=True)[1:]
@@ -121,8 +126,9 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": "Mray/s on 46-sphere scene @1280x720", "value": value, "unit": "Mray/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "threads": cores},
-            "cpu_baseline": {"value": value, "unit": "Mray/s", "cores": cores, "kind": kind,
+            "config": {"workload": WORKLOAD, "mode": "reference C++ SIMD path (enkiTS, all hardware threads)", "parallelism": "host CPU",
+                       "l2": None, "timing": "steady clock around UpdateTest+DrawTest per frame", "threads": os.cpu_count()},
+            "cpu_baseline": {"value": value, "unit": "Mray/s", "cores": cores, "kind": kind, "host": cpu_info,
                              "sample": f"{args.steps} frames of 1280x720x4spp after {max(2, args.warmup)} warm-up frames, "
                                        "UpdateTest+DrawTest per frame, steady clock"},
             "e2e": {"value": value, "unit": "Mray/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -134,7 +140,7 @@ def cpu_baseline_sample():
     """Bounded sample of the reference CPU path on this box's host cores (rank 0, N=1 only): ~10-20 s."""
     from oracle import pyoracle
     kind = "reference" if pyoracle.have_ref() else "port"
-    cores = os.cpu_count() or 1
+    cores, cpu_info = usable_cores()
     buf = np.zeros((H, W, 4), np.float32)
     if kind == "reference":
         run = lambda f0, n: pyoracle.ref_render(W, H, f0, n, flags=0, buf=buf, want_seconds=True)[1:]
@@ -150,9 +156,46 @@ def cpu_baseline_sample():
         rays += r; secs += s; frames += 8
     # median frame (discard warm-up, median of >= 30 frames)
     per_frame = sorted(r / s / 1e6 for r, s in zip(rays, secs))
-    return {"value": per_frame[len(per_frame) // 2], "unit": "Mray/s", "cores": cores, "kind": kind,
+    return {"value": per_frame[len(per_frame) // 2], "unit": "Mray/s", "cores": cores, "kind": kind, "host": cpu_info,
+            "threads_spawned": os.cpu_count(),
             "sample": f"median of {frames} frames of 1280x720x4spp (UpdateTest+DrawTest each) after 3 warm-up frames; "
                       f"mean {sum(rays) / sum(secs) / 1e6:.1f} Mray/s"}
+
+
+def host_cpu_info():
+    """What the CPU arm can really use on this box: os.cpu_count() reports the machine, not the lease."""
+    info = {"os_cpu_count": os.cpu_count()}
+    try:
+        info["sched_affinity"] = len(os.sched_getaffinity(0))
+    except Exception:
+        info["sched_affinity"] = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            info["cgroup_cpu_max"] = open(path).read().strip()
+            break
+        except Exception:
+            info["cgroup_cpu_max"] = None
+    try:
+        info["loadavg"] = os.getloadavg()[0]
+    except Exception:
+        pass
+    return info
+
+
+def usable_cores():
+    info = host_cpu_info()
+    n = info.get("sched_affinity") or info["os_cpu_count"] or 1
+    q = info.get("cgroup_cpu_max")
+    if q:
+        parts = q.split()
+        try:
+            if len(parts) == 2 and parts[0] != "max":
+                n = min(n, max(1, int(float(parts[0]) / float(parts[1]) + 0.5)))
+            elif len(parts) == 1 and int(parts[0]) > 0:
+                n = min(n, max(1, int(int(parts[0]) / 100000 + 0.5)))
+        except Exception:
+            pass
+    return n, info
 
 
 def main():
@@ -164,6 +207,7 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
     ap.add_argument("--variant", type=int, default=-1, help="fast kernel variant (default: library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the 3840x2160x64spp strong-scaling sub-record (N > 1)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -193,105 +237,152 @@ def main():
     if args.variant >= 0:
         ctx.set_option("fast_variant", args.variant)
     mode = tpt.MODE_FAST if args.mode == "fast" else tpt.MODE_EXACT
-    # flags = 0 exactly like the reference step; at N > 1 rank r renders global frame s*N + r.
-    image = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     stream = torch.cuda.Stream(dev)          # a real (non-NULL) stream: the library treats NULL as "my own stream"
     torch.cuda.set_stream(stream)
     sh = stream.cuda_stream
 
-    def step(s, timed_events=None):
-        frame = s * world + rank
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # N = 1: one frame per step, flags = 0 (the reference step). N > 1: north_star's tiled image split — step s renders
+    # the N frames s*N .. s*N+N-1 of ONE 1280x720 image (accumulated with kFlagProgressive, every sample contributes),
+    # rank r traces rows r, r+N, ... of all N frames into its packed band, and ONE all_gather per step assembles the
+    # 14.7 MB image on every rank inside the timed region. Per-GPU work per step is one frame's worth at every N.
+    row0, nrows, rstep = mg.rows_of_rank(H, rank, world)
+    if world == 1:
+        image = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+    else:
+        band = torch.zeros((nrows, W, 4), dtype=torch.float32, device=dev)
+    assembled = [None]
+
+    def step(s, evs=None):
         flush.fill_(s & 0xFF)                                             # L2 flush, outside the timed events
-        if timed_events is not None:
-            timed_events[0].record(stream)
-        ctx.draw(frame, 1, W, H, image, flags=0, mode=mode, stream=sh, want_rays=False)
-        if timed_events is not None:
-            timed_events[1].record(stream)
+        if evs is not None:
+            evs[0].record(stream)
+        if world == 1:
+            ctx.draw(s, 1, W, H, image, flags=0, mode=mode, stream=sh, want_rays=False)
+            if evs is not None:
+                evs[1].record(stream)
+        else:
+            ctx.draw(s * world, world, W, H, band, flags=tpt.kFlagProgressive, mode=mode, rows=(row0, nrows, rstep, 1),
+                     stream=sh, want_rays=False)
+            if evs is not None:
+                evs[1].record(stream)
+            assembled[0] = mg.gather_rows(band, H, rank, world)           # the exchange step, every step
+        if evs is not None:
+            evs[2].record(stream)
 
     for s in range(args.warmup):
         step(s)
-    if world > 1:
-        dist.all_reduce(image, op=dist.ReduceOp.SUM)                      # warm-up includes the exchange step (NCCL sets up
-        dist.all_reduce(image, op=dist.ReduceOp.SUM)                      # its buffers / NVLS on the first large collective)
     ctx.read_ray_count(sh)                                                # reset the accumulated counter
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kernel_ms = []
+        sampler.start()                                                   # BEFORE the barrier: no rank enters the timed region late
+        time.sleep(0.2)
+    barrier()
+    evs = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(args.steps)]
     wall0 = time.perf_counter()
     for s in range(args.steps):
         step(args.warmup + s, evs[s])
-    extra = None
-    if world > 1:
-        extra = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        extra[0].record(stream)
-        # the exchange step of the frame-sharded accumulation: one all_reduce(sum) of the image
-        dist.all_reduce(image, op=dist.ReduceOp.SUM)
-        extra[1].record(stream)
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
+    barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if rank == 0 else None
-    step_ms = [a.elapsed_time(b) for a, b in evs]
-    dev_ms = sum(step_ms) + (extra[0].elapsed_time(extra[1]) if extra else 0.0)
+    step_ms = [a.elapsed_time(c) for a, b, c in evs]
+    kernel_step_ms = [a.elapsed_time(b) for a, b, c in evs]
+    exchange_ms = [b.elapsed_time(c) for a, b, c in evs]
+    my_ms = sum(step_ms)
+    dev_ms = my_ms
     rays = ctx.read_ray_count(sh)
     launches = ctx.last_launch_count() * args.steps
+    per_rank_ms = [my_ms]
 
     if world > 1:
-        t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms = float(t.item())
+        t = torch.tensor([my_ms], dtype=torch.float64, device=dev)
+        allt = torch.zeros(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allt, t)
+        per_rank_ms = [float(x) for x in allt.cpu()]
+        dev_ms = max(per_rank_ms)
         rays = mg.sum_ray_counts(rays, dev)
         lt = torch.tensor([launches], dtype=torch.int64, device=dev); dist.all_reduce(lt); launches = int(lt.item())
 
-    # ---- end to end through the C-ABI with host buffers (every rank; rank 0 reports the max time)
+    # ---- end to end through the C-ABI (every rank; the slowest rank's wall time counts)
     e2e_steps = min(args.steps, 50)
-    host = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory().numpy()
-    for s in range(3):
-        ctx.set_scene(sph, mats, cam, em)
-        ctx.draw(s * world + rank, 1, W, H, host, flags=0, mode=mode)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    e2e_rays = 0
-    for s in range(e2e_steps):
-        ctx.set_scene(sph, mats, cam, em)                                  # scene H2D (UpdateTest + upload)
-        e2e_rays += ctx.draw((args.warmup + s) * world + rank, 1, W, H, host, flags=0, mode=mode)  # kernel + image D2H + count D2H
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
+    scene_bytes = 46 * 20 + 46 * 36 + 88 + 2 * 4
+    if world == 1:
+        # host backbuffer in, host backbuffer out: what a reference shell does per frame
+        host = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory().numpy()
+        for s in range(3):
+            ctx.set_scene(sph, mats, cam, em)
+            ctx.draw(s, 1, W, H, host, flags=0, mode=mode)
+        t0 = time.perf_counter()
+        e2e_rays = 0
+        for s in range(e2e_steps):
+            ctx.set_scene(sph, mats, cam, em)                              # scene H2D (UpdateTest + upload)
+            e2e_rays += ctx.draw(args.warmup + s, 1, W, H, host, flags=0, mode=mode)  # kernel + image D2H + count D2H
+        e2e_s = time.perf_counter() - t0
+        h2d = scene_bytes + (W * H * 16 if mode == tpt.MODE_EXACT else 0)  # exact mode uploads prev (bit parity)
+        d2h = W * H * 16 + 8
+        e2e_api = "tpt_set_scene + tpt_draw(host backbuffer) per step, wall clock"
+    else:
+        # per step: scene H2D on every rank, tpt_draw of the rank's rows (band resident in HBM: it is the accumulation
+        # state, not a per-step input), all_gather, and rank 0 reads the assembled image + every rank its ray count back
+        host = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory()
+        band.zero_()
+        def e2e_step(s):
+            ctx.set_scene(sph, mats, cam, em)
+            r = ctx.draw(s * world, world, W, H, band, flags=tpt.kFlagProgressive, mode=mode, rows=(row0, nrows, rstep, 1), stream=sh)
+            img = mg.gather_rows(band, H, rank, world)
+            if rank == 0:
+                host.copy_(img, non_blocking=True)
+            stream.synchronize()
+            return r
+        for s in range(3):
+            e2e_step(s)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_rays = 0
+        for s in range(e2e_steps):
+            e2e_rays += e2e_step(3 + s)
+        barrier()
+        e2e_s = time.perf_counter() - t0
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
         e2e_rays = mg.sum_ray_counts(e2e_rays, dev)
-    scene_bytes = 46 * 20 + 46 * 36 + 88 + 2 * 4
-    h2d = scene_bytes + (W * H * 16 if mode == tpt.MODE_EXACT else 0)      # exact mode uploads prev (bit parity)
-    d2h = W * H * 16 + 8
+        h2d = scene_bytes * world
+        d2h = W * H * 16 + 8 * world
+        e2e_api = ("per step and rank: tpt_set_scene + tpt_draw(rows rank::N of N frames, device band) + all_gather; "
+                   "rank 0 copies the assembled image to pinned host memory; wall clock, max over ranks")
+
+    strong = None
+    if world > 1 and args.mode == "fast" and not args.no_strong:
+        strong = strong_scaling_record(ctx, tpt, mg, torch, dist, dev, stream, rank, world)
 
     if rank == 0:
         hbm_peak, peak_src = load_peaks()
         value = rays / (dev_ms * 1e-3) / 1e6
-        kms = statistics.mean(step_ms)
-        alg_bytes = W * H * 16                                             # one float4 per pixel written, flags=0: no read
+        kms = statistics.mean(kernel_step_ms)
+        alg_bytes = (W * H * 16 + (W * H * 4 if world == 1 else W * H * 16)) // world   # float4 written (+ alpha / prev read)
         achieved = alg_bytes / (kms * 1e-3) / 1e9
         tests_per_s = (rays / world / args.steps) * (SPHERES + 2) / (kms * 1e-3)   # 48 padded spheres swept per ray
         line = {
             "metric": "Mray/s on 46-sphere scene @1280x720", "value": value, "unit": "Mray/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "mode": args.mode, "parallelism": f"frames x{world}" if world > 1 else "1 GPU",
+            "config": {"workload": WORKLOAD, "mode": args.mode,
+                       "parallelism": (f"image rows interleaved over {world} GPUs, {world} frames per step accumulated "
+                                       f"(kFlagProgressive), all_gather of the 14.7 MB image every step") if world > 1 else "1 GPU",
                        "l2": "flushed between steps (256 MiB fill), not timed",
-                       "timing": "CUDA events per step on the launching stream, summed; max over ranks"},
+                       "timing": "CUDA events per step on the launching stream (draw + exchange), summed; max over ranks",
+                       "threads": None},
             "clocks": clocks,
+            "per_rank_ms": per_rank_ms,
+            "exchange_ms_per_step": statistics.mean(exchange_ms) if world > 1 else 0.0,
+            "kernel_ms_per_step": kms,
             "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mray/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                    "api": "tpt_set_scene + tpt_draw(host backbuffer) per step, wall clock"},
+                    "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps, "api": e2e_api},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": load_traffic() if args.mode == "fast" else None, "peak_source": peak_src,
@@ -304,6 +395,8 @@ def main():
                                   "peak_def": "148 SM x 128 lanes x 1.965 GHz / 17 FP32 issue slots per test (no FMA)"}},
             "wall_s": wall,
         }
+        if strong is not None:
+            line["strong"] = strong
         if world == 1 and args.mode == "fast":
             # the bit-exact mode on the same step, for the record (same API, same buffers; latency-bound: one serial RNG
             # chain per image row, Test.cpp:280)
@@ -328,7 +421,77 @@ def main():
                 line["cpu_baseline"] = {"error": str(ex)}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def strong_scaling_record(ctx, tpt, mg, torch, dist, dev, stream, rank, world):
+    """BASELINE configs[3]: ONE 3840x2160 image at 64 spp (frames 0..15), rows interleaved over the ranks.
+      one_gpu_ms  rank 0 renders the whole image alone (the other ranks idle)
+      A           every rank renders its packed band (k_fast_queue) + ONE NCCL all_gather assembles it on every rank
+      B           every rank's tile kernel (k_fast_tileq) stores its finished tiles straight into rank 0's image over
+                  NVLink (CUDA IPC peer mapping): render and gather fused, a 4-byte all_reduce as completion barrier
+    Device time (CUDA events on the launching stream) between barriers, max over ranks, best of 3."""
+    w, h, nf, reps = 3840, 2160, 16, 3
+    sh = stream.cuda_stream
+    ctx.set_scene(*tpt.reference_scene(w, h))
+    row0, nrows, rstep = mg.rows_of_rank(h, rank, world)
+
+    def timed(fn, everyone=True):
+        best = None
+        for rep in range(reps + 1):                                # first repetition = warm-up
+            torch.cuda.synchronize(dev); dist.barrier(); torch.cuda.synchronize(dev)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            if everyone or rank == 0:
+                fn()
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if rep > 0:
+                best = t.item() if best is None else min(best, t.item())
+        return best
+
+    ctx.set_option("fast_variant", 3)
+    full = torch.zeros((h, w, 4), dtype=torch.float32, device=dev) if rank == 0 else None
+    ctx.read_ray_count(sh)
+    one_ms = timed(lambda: ctx.draw(0, nf, w, h, full, flags=2, mode=tpt.MODE_FAST, stream=sh, want_rays=False), everyone=False)
+    rays = mg.sum_ray_counts(ctx.read_ray_count(sh), dev) // (reps + 1)
+    del full
+    band = torch.zeros((nrows, w, 4), dtype=torch.float32, device=dev)
+    out = [None]
+    def method_a():
+        ctx.draw(0, nf, w, h, band, flags=2, mode=tpt.MODE_FAST, rows=(row0, nrows, rstep, 1), stream=sh, want_rays=False)
+        out[0] = mg.gather_rows(band, h, rank, world)
+    a_ms = timed(method_a)
+    rays_a = mg.sum_ray_counts(ctx.read_ray_count(sh), dev) // (reps + 1)
+    img_a = out[0]
+    ctx.set_option("fast_variant", 5)
+    ctx.set_option("fast_alpha_zero", 1)                           # the peer image is write-only for the other ranks
+    shared = mg.SharedImage(ctx, w, h, rank)
+    done = torch.zeros(1, device=dev)
+    def method_b():
+        ctx.draw(0, nf, w, h, shared.ptr, flags=2, mode=tpt.MODE_FAST, rows=(row0, nrows, rstep, 0), stream=sh, want_rays=False)
+        dist.all_reduce(done)
+    b_ms = timed(method_b)
+    rays_b = mg.sum_ray_counts(ctx.read_ray_count(sh), dev) // (reps + 1)
+    rel = None
+    if rank == 0:
+        import numpy as _np
+        b = shared.to_host()[..., :3].astype(_np.float64)
+        a = img_a.cpu().numpy()[..., :3].astype(_np.float64)
+        rel = float(_np.sqrt(((a - b) ** 2).sum() / (a ** 2).sum()))
+    dist.barrier()
+    shared.close()
+    ctx.set_option("fast_variant", 3)
+    ctx.set_option("fast_alpha_zero", 0)
+    ctx.set_scene(*tpt.reference_scene(W, H))
+    return {"workload": "46 spheres, 3840x2160, 64 spp (frames 0..15) — BASELINE configs[3]; rows interleaved over the ranks",
+            "rays": rays, "one_gpu_ms": one_ms, "one_gpu_mray_s": rays / one_ms / 1e3,
+            "A_nccl_allgather": {"ms": a_ms, "mray_s": rays_a / a_ms / 1e3, "speedup_vs_one_gpu": one_ms / a_ms, "kernel": "k_fast_queue"},
+            "B_fused_peer_writeout": {"ms": b_ms, "mray_s": rays_b / b_ms / 1e3, "speedup_vs_one_gpu": one_ms / b_ms, "kernel": "k_fast_tileq"},
+            "relL2_A_vs_B": rel, "timing": "CUDA events between barriers, max over ranks, best of 3 after one warm-up"}
 
 
 if __name__ == "__main__":

@@ -55,6 +55,7 @@ def orc_lib():
             build()
         L = ctypes.CDLL(ORC_SO)
         L.orc_render.restype = ctypes.c_int
+        L.orc_render_rows.restype = ctypes.c_int
         _orc = L
     return _orc
 
@@ -87,9 +88,10 @@ def ref_scene(w, h, time=0.0, flags=0):
 
 
 def orc_render(spheres, mats, cam, w, h, frame0, nframes, flags=0, spp=4, simd_tie=1, buf=None, nthreads=0,
-               want_seconds=False):
+               want_seconds=False, rows=None):
     """CPU restatement on an arbitrary scene. Returns (buf, rays per frame, pad pixel list [(x,y,frame)...]
-    [, seconds per frame])."""
+    [, seconds per frame]). rows = (row0, numRows, rowStep): only those rows are traced (into their place in the
+    full-size buf) and counted."""
     L = orc_lib()
     spheres = np.ascontiguousarray(spheres); mats = np.ascontiguousarray(mats); cam = np.ascontiguousarray(cam)
     n = spheres.nbytes // 20
@@ -101,8 +103,10 @@ def orc_render(spheres, mats, cam, w, h, frame0, nframes, flags=0, spp=4, simd_t
     pad = ctypes.c_longlong(0)
     cap = 4096
     padxy = np.zeros((cap, 3), np.int32)
-    L.orc_render(_vp(spheres), _vp(mats), n, _vp(cam), w, h, frame0, nframes, ctypes.c_uint(flags), spp, simd_tie,
-                 _vp(buf), rays, ctypes.byref(pad), secs, nthreads, _vp(padxy), cap)
+    row0, nrows, rstep = rows if rows is not None else (0, h, 1)
+    assert nrows >= 0 and rstep >= 1 and row0 >= 0 and (nrows == 0 or row0 + (nrows - 1) * rstep < h)
+    L.orc_render_rows(_vp(spheres), _vp(mats), n, _vp(cam), w, h, frame0, nframes, ctypes.c_uint(flags), spp, simd_tie,
+                      _vp(buf), rays, ctypes.byref(pad), secs, nthreads, _vp(padxy), cap, row0, nrows, rstep)
     pads = [tuple(int(v) for v in p) for p in padxy[: min(pad.value, cap)]]
     out = (buf, [int(r) for r in rays], pads)
     return out + ([float(s) for s in secs],) if want_seconds else out

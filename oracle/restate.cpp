@@ -392,10 +392,12 @@ extern "C" {
 // (UpdateTest + DrawTest per frame) into buf (w*h*4, caller-owned, read as `prev`).
 // rays[i] = rays of frame i; pad_hits (optional) = number of path rays that hit a padded sphere (reference
 // UB, see Trace()); pad_xyf (optional, pad_cap triples) = (x, y, frame) of the pixels those rays belong to.
-int orc_render(const float* spheres, const void* mats, int count, const void* cam,
+// orc_render_rows: the same over the rows y_i = row0 + i*row_step, i in [0, num_rows) only (TraceRowJob(start,end)
+// generalised the way tpt_draw's row shards are); the other rows of buf are not touched and not counted.
+int orc_render_rows(const float* spheres, const void* mats, int count, const void* cam,
                int w, int h, int frame0, int nframes, unsigned flags, int spp, int simd_tie,
                float* buf, long long* rays, long long* pad_hits, double* seconds, int nthreads,
-               int* pad_xyf, int pad_cap)
+               int* pad_xyf, int pad_cap, int row0, int num_rows, int row_step)
 {
     PadLog padLog; padLog.n = 0; padLog.cap = pad_xyf ? pad_cap : 0; padLog.xyf = pad_xyf;
     Scene sc;
@@ -431,10 +433,10 @@ int orc_render(const float* spheres, const void* mats, int count, const void* ca
             long long myRays = 0, myPad = 0;
             for (;;)
             {
-                int y0 = nextRow.fetch_add(4); // Test.cpp:359 min range 4 rows
-                if (y0 >= h) break;
-                for (int y = y0; y < y0 + 4 && y < h; ++y)
-                    TraceRow(sc, y, frame0 + f, w, h, flags, spp, buf, myRays, myPad, &padLog);
+                int i0 = nextRow.fetch_add(4); // Test.cpp:359 min range 4 rows
+                if (i0 >= num_rows) break;
+                for (int i = i0; i < i0 + 4 && i < num_rows; ++i)
+                    TraceRow(sc, row0 + i * row_step, frame0 + f, w, h, flags, spp, buf, myRays, myPad, &padLog);
             }
             rc += myRays; ph += myPad;
         };
@@ -449,6 +451,15 @@ int orc_render(const float* spheres, const void* mats, int count, const void* ca
     }
     if (pad_hits) *pad_hits = padTotal;
     return 0;
+}
+
+int orc_render(const float* spheres, const void* mats, int count, const void* cam,
+               int w, int h, int frame0, int nframes, unsigned flags, int spp, int simd_tie,
+               float* buf, long long* rays, long long* pad_hits, double* seconds, int nthreads,
+               int* pad_xyf, int pad_cap)
+{
+    return orc_render_rows(spheres, mats, count, cam, w, h, frame0, nframes, flags, spp, simd_tie, buf, rays, pad_hits,
+                           seconds, nthreads, pad_xyf, pad_cap, 0, h, 1);
 }
 
 // libm probes so tests can pin the product's device-side glibc restatement against the very libm

@@ -318,7 +318,7 @@ int tpt_set_option(tpt_context* ctx, const char* key, int value)
 {
     if (!ctx || !key) return (int)cudaErrorInvalidValue;
     if (!strcmp(key, "fast_variant")) { if (value < 0 || value > 7) return fail_msg(ctx, "fast_variant: 0..7"); ctx->fastVariant = value; return 0; }
-    if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 8 && value != 9 && value != 32) return fail_msg(ctx, "exact_lanes: 0,1,2,8,9,32"); ctx->exactLanes = value; return 0; }
+    if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 8 && value != 9 && value != 32 && value != 64 && value != 65) return fail_msg(ctx, "exact_lanes: 0,1,2,8,9,32,64,65"); ctx->exactLanes = value; return 0; }
     if (!strcmp(key, "register_host")) { ctx->registerHost = value ? 1 : 0; return 0; }
     if (!strcmp(key, "fast_kform")) { ctx->fastKForm = value ? 1 : 0; return 0; }
     if (!strcmp(key, "fast_alpha_zero")) { ctx->fastAlphaZero = value ? 1 : 0; return 0; }

@@ -157,6 +157,212 @@ __global__ void k_resolve_exact(DrawParams p)
     *px = prev;
 }
 
+
+// ---- split kernel: one PATH warp + H SHADE warps per chain ----------------------------------------------------------------
+// One 4-spp frame is only `height` chains, and a chain is a serial dependency through its RNG stream — but only through
+// ray generation, the sweep and the scatter direction (see xpath_sample). Everything else (explicit light sampling with
+// its shadow-ray sweeps — 44 % of all rays —, emission/attenuation, the back-to-front fold, the blend and the store) is
+// taken off that critical path: warp 0 of the CTA walks the chain and pushes one 48-byte event per path vertex into a
+// shared-memory ring (mbarrier full/empty pairs per slot); shade warp h consumes the samples k with k % H == h:
+//   * the lights of a Lambert vertex are sampled by the two HALF-warps at once (light j on lanes 0-15, light j+1 on lanes
+//     16-31, each half sweeping the spheres 16-wide and reducing its nearest hit with REDUX under its own mask),
+//     contributions added in the reference's light order;
+//   * finished samples go to a per-pixel slot; the warp that completes a pixel sums them in sample order (Test.cpp:289-291),
+//     blends (Test.cpp:293-295) and stores the float4.
+// Bit parity: tests/test_host_sim.py (the same xpath_sample/xshade_event on the host) and tests/test_gpu_exact.py.
+constexpr int kRingDepth = 16;      // events per shade warp in flight
+constexpr int kPixSlots = 16;       // pixels whose samples may be in flight (see the capacity argument in DESIGN.md)
+constexpr int kSplitMaxSpp = 8;
+
+struct __align__(16) XEventSlot { float4 q0, q1, q2; };
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int H>
+__global__ void __launch_bounds__(32 * (1 + H))
+k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights, uint32_t stagedBytes)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint64_t fullBar[H][kRingDepth], emptyBar[H][kRingDepth];
+    __shared__ XEventSlot ring[H][kRingDepth];
+    __shared__ float pixRes[kPixSlots][kSplitMaxSpp][3];
+    __shared__ unsigned pixCnt[kPixSlots];
+    stage_blob(smem, blob, stagedBytes, &bar);
+    if (threadIdx.x == 0)
+    {
+        for (int h = 0; h < H; ++h)
+            for (int i = 0; i < kRingDepth; ++i) { mbar_init(&fullBar[h][i], 1); mbar_init(&emptyBar[h][i], 1); }
+        mbar_fence_init();
+    }
+    if (threadIdx.x < kPixSlots) pixCnt[threadIdx.x] = 0;
+    __syncthreads();
+    SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long chain = blockIdx.x;
+    // same chain order as k_trace_exact: consecutive chains = the same row in consecutive frames
+    const int ri = (int)(chain / p.numFrames), fi = (int)(chain % p.numFrames);
+    const int y = p.row0 + ri * p.rowStep;
+    const int frame = p.frame0 + fi;
+    const int spp = p.spp;
+    const uint32_t totalSamples = (uint32_t)p.width * (uint32_t)spp;
+
+    if (warp == 0)
+    {
+        // ---- PATH warp: the chain's RNG stream, sweeps split over the 32 lanes
+        GroupHitter<true, 32> hitter;
+        hitter.sub = lane; hitter.mask = 0xffffffffu;
+        uint32_t rng = row_seed(y, frame);
+        unsigned rc = 0;
+        uint32_t seq[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) seq[h] = 0;
+        uint32_t k = 0;
+        for (int x = 0; x < p.width; ++x)
+            for (int s = 0; s < spp; ++s, ++k)
+            {
+                const int h = H == 1 ? 0 : (int)(k % (uint32_t)H);
+                xpath_sample(sc, p.cam, x, y, p.invWidth, p.invHeight, rng, rc, hitter,
+                             [&](int type, int mid, V3 a, V3 b, V3 c, uint32_t erng) {
+                                 uint32_t sq = 0;
+#pragma unroll
+                                 for (int hh = 0; hh < H; ++hh) if (hh == h) sq = seq[hh];
+                                 const uint32_t slot = sq % kRingDepth, phase = (sq / kRingDepth) & 1u;
+                                 mbar_wait(&emptyBar[h][slot], phase ^ 1u);      // slot free (passes at once on a fresh barrier)
+                                 if (lane == 0)
+                                 {
+                                     XEventSlot& e = ring[h][slot];
+                                     e.q0 = make_float4(a.x, a.y, a.z, __int_as_float(type | (mid << 2)));
+                                     e.q1 = make_float4(b.x, b.y, b.z, __uint_as_float(erng));
+                                     e.q2 = make_float4(c.x, c.y, c.z, 0.0f);
+                                     mbar_arrive(&fullBar[h][slot]);            // release: the stores above are visible to the waiter
+                                 }
+#pragma unroll
+                                 for (int hh = 0; hh < H; ++hh) if (hh == h) seq[hh] = sq + 1;
+                             });
+            }
+        if (lane == 0) atomicAdd(p.rayCounter + fi, (unsigned long long)rc);
+        return;
+    }
+
+    // ---- SHADE warp h: samples k = h, h + H, ...
+    const int h = warp - 1;
+    const int grp = lane >> 4;                                   // half-warp = one light
+    GroupHitter<true, 16> hitter;
+    hitter.sub = lane & 15; hitter.mask = 0xffffu << (grp * 16);
+    const float lerpFac = lerp_fac(frame, p.flags);
+    const float oneMinus = 1.0f - lerpFac;
+    const float invSpp = M<true>::div_(1.0f, (float)spp);
+    const size_t imgRow = (size_t)(p.packed ? ri : y) * p.width;
+    uint32_t seq = 0;
+
+    auto lights = [&](int mid, V3 pos, V3 normal, V3 rdir, V3 albedo, uint32_t rng) -> V3 {
+        V3 lightE = v3(0, 0, 0);
+        int myJ = -1, kk = 0;
+        uint32_t myRng = 0;
+        auto run_batch = [&]() {
+            V3 contrib = v3(0, 0, 0);
+            bool reached = false;
+            if (myJ >= 0)
+            {
+                const LightRec Lr = sc.lights[myJ];
+                V3 l;
+                sample_light<true>(Lr, pos, normal, rdir, albedo, myRng, l, contrib);
+                float ts;
+                reached = hitter.hit(sc, pos, l, TPT_MIN_T, TPT_MAX_T, ts) == Lr.id;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < 2; ++g)                            // the reference's light order (Test.cpp:96)
+            {
+                const bool r = __shfl_sync(0xffffffffu, reached ? 1 : 0, g * 16) != 0;
+                const V3 cg = v3(__shfl_sync(0xffffffffu, contrib.x, g * 16), __shfl_sync(0xffffffffu, contrib.y, g * 16),
+                                 __shfl_sync(0xffffffffu, contrib.z, g * 16));
+                if (r) lightE = lightE + cg;
+            }
+            myJ = -1;
+        };
+        for (int j = 0; j < sc.nLights; ++j)
+        {
+            if (sc.lights[j].id == mid) continue;                  // Test.cpp:100
+            if ((kk & 1) == grp) { myJ = j; myRng = rng; }
+            XorShift32(rng); XorShift32(rng);                      // eps1, eps2 of this light (Test.cpp:112)
+            if ((++kk & 1) == 0) run_batch();
+        }
+        if (kk & 1) run_batch();
+        return lightE;
+    };
+
+    for (uint32_t k = (uint32_t)h; k < totalSamples; k += (uint32_t)H)
+    {
+        const int x = (int)(k / (uint32_t)spp), s = (int)(k - (uint32_t)x * (uint32_t)spp);
+        XShade sh;
+        xshade_begin(sh);
+        V3 result;
+        for (;;)
+        {
+            const uint32_t slot = seq % kRingDepth, phase = (seq / kRingDepth) & 1u;
+            mbar_wait(&fullBar[h][slot], phase);
+            const XEventSlot& e = ring[h][slot];
+            const float4 q0 = e.q0, q1 = e.q1, q2 = e.q2;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&emptyBar[h][slot]);
+            ++seq;
+            const int tm = __float_as_int(q0.w);
+            if (xshade_event(sc, sh, tm & 3, tm >> 2, v3(q0.x, q0.y, q0.z), v3(q1.x, q1.y, q1.z), v3(q2.x, q2.y, q2.z),
+                             __float_as_uint(q1.w), lights, result)) break;
+        }
+        // hand the sample to its pixel; whoever completes the pixel finishes it
+        const int ps = x % kPixSlots;
+        unsigned old = 0;
+        if (lane == 0)
+        {
+            pixRes[ps][s][0] = result.x; pixRes[ps][s][1] = result.y; pixRes[ps][s][2] = result.z;
+            __threadfence_block();
+            old = atomicInc(&pixCnt[ps], (unsigned)spp - 1u);      // wraps to 0 with the pixel's last sample
+        }
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old == (unsigned)spp - 1u && lane == 0)
+        {
+            __threadfence_block();
+            V3 col = v3(0, 0, 0);
+            for (int t = 0; t < spp; ++t)
+                col = col + v3(((volatile float*)pixRes[ps][t])[0], ((volatile float*)pixRes[ps][t])[1], ((volatile float*)pixRes[ps][t])[2]);
+            col = col * invSpp;                                    // Test.cpp:291
+            if (p.numFrames == 1)
+            {
+                float4* px = reinterpret_cast<float4*>(p.image + (imgRow + x) * 4);
+                float4 prev = *px;
+                prev.x = prev.x * lerpFac + col.x * oneMinus;      // Test.cpp:293-295, alpha untouched
+                prev.y = prev.y * lerpFac + col.y * oneMinus;
+                prev.z = prev.z * lerpFac + col.z * oneMinus;
+                *px = prev;
+            }
+            else
+            {
+                float4* px = reinterpret_cast<float4*>(p.scratch) + ((size_t)fi * p.numRows + ri) * p.width + x;
+                *px = make_float4(col.x, col.y, col.z, 0.0f);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int H>
+static cudaError_t launch_exact_split_t(const DrawParams& p, const SceneDev& sc, cudaStream_t stream)
+{
+    const long long totalChains = (long long)p.numRows * p.numFrames;
+    auto kern = k_trace_exact_split<H>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc.stagedBytes);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)totalChains, 32 * (1 + H), sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes);
+    return cudaGetLastError();
+}
+
 template <int LANES>
 static cudaError_t launch_exact_t(const DrawParams& p, const SceneDev& sc, cudaStream_t stream, int blockThreads)
 {
@@ -204,6 +410,10 @@ cudaError_t launch_exact(const DrawParams& p, const SceneDev& sc, int lanes, cud
     case 9: e = launch_exact_flat_t<8>(p, sc, stream); break;        // flat form with 8 lanes per chain: measured 2x SLOWER than
                                                                      // the nested form at 11 520 chains (221 vs 111 ms), comparison only
     case 32: e = launch_exact_t<32>(p, sc, stream, block); break;
+    case 64: case 65:                                                // split kernel: path warp + 1 or 2 shade warps per chain
+        if (p.spp > kSplitMaxSpp || totalChains > 0x7fffffffLL) return cudaErrorInvalidValue;
+        e = lanes == 64 ? launch_exact_split_t<1>(p, sc, stream) : launch_exact_split_t<2>(p, sc, stream);
+        break;
     default: return cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return e;

@@ -730,3 +730,121 @@ TPT_HD bool xchain_step(const SceneView& sc, const Camera88& cam, XChain& c, int
 }
 
 } // namespace tpt
+
+// ---- split form of the exact path: a PATH stream (geometry + RNG, no colour arithmetic) and a SHADE stream -----------------
+// The serial dependency of the reference's per-row RNG chain (Test.cpp:280) runs through ray generation, the sphere sweep
+// and the scatter DIRECTION only: which draws a sample consumes never depends on a colour, on a shadow ray's result or
+// on the fold of Test.cpp:216. xpath_sample() therefore walks one camera sample with exactly the reference's RNG draw
+// order and emits one event per path vertex; xshade_event() consumes the events later (on another warp, tpt_exact.cu
+// k_trace_exact_split) and does everything the RNG chain does not wait for: explicit light sampling incl. the shadow
+// rays (Test.cpp:96-133; its draws are taken from the state snapshot the event carries, the path stream only skips
+// them), emission/attenuation bookkeeping (Test.cpp:207-221) and the back-to-front fold (Test.cpp:216). Same
+// arithmetic, same order per quantity => the same bits as trace_exact().
+namespace tpt {
+
+enum { XE_LAMBERT = 0, XE_SPEC = 1, XE_END_SKY = 2, XE_END_MATE = 3 };
+
+// One camera sample (Test.cpp:286-288 + Trace). emit(type, mid, a, b, c, rng):
+//   XE_LAMBERT  a = pos, b = normal, c = incoming dir, rng = state BEFORE the light-sampling draws
+//   XE_SPEC     Metal / Dielectric vertex that scattered (attenuation follows from the material)
+//   XE_END_SKY  a = dir of the ray that missed everything           (sample ends)
+//   XE_END_MATE depth limit or failed scatter: result = emissive    (sample ends, Test.cpp:218-221)
+template <class Hitter, class Emit>
+TPT_D void xpath_sample(const SceneView& sc, const Camera88& cam, int x, int y, float invWidth, float invHeight,
+                        uint32_t& rng, unsigned& rayCount, const Hitter& hitter, Emit&& emit)
+{
+    float u = ((float)x + RandomFloat01(rng)) * invWidth;
+    float v = ((float)(uint32_t)y + RandomFloat01(rng)) * invHeight;
+    Ray r = GetRay<true>(cam, u, v, rng);
+    const V3 zero = v3(0, 0, 0);
+    for (int depth = 0;; ++depth)
+    {
+        ++rayCount;
+        float t;
+        const int id = hitter.hit(sc, r.orig, r.dir, TPT_MIN_T, TPT_MAX_T, t);
+        if (id < 0) { emit(XE_END_SKY, 0, r.dir, zero, zero, 0u); return; }
+        Q4 s = ld_sph(sc, id);
+        V3 pos = r.orig + r.dir * t;
+        V3 normal = (pos - v3(s.x, s.y, s.z)) * sc.invRadius[id];
+        const int mid = id < sc.count ? id : sc.count;
+        if (depth >= TPT_MAX_DEPTH) { emit(XE_END_MATE, mid, zero, zero, zero, 0u); return; }
+        Mat mat = load_mat(sc, mid);
+        if (mat.type == kLambert)
+        {
+            V3 target = pos + normal + RandomUnitVector<true>(rng);       // Test.cpp:89-92
+            V3 outDir = M<true>::normalize(target - pos);
+            const uint32_t rngLights = rng;
+            for (int j = 0; j < sc.nLights; ++j)                          // Test.cpp:96-122: 2 draws + 1 ray per light
+                if (sc.lights[j].id != mid) { XorShift32(rng); XorShift32(rng); ++rayCount; }
+            emit(XE_LAMBERT, mid, pos, normal, r.dir, rngLights);
+            r.orig = pos; r.dir = outDir;
+        }
+        else
+        {
+            V3 attenuation, outDir;
+            if (!scatter_specular<true>(mat, r.dir, pos, normal, rng, attenuation, outDir)) { emit(XE_END_MATE, mid, zero, zero, zero, 0u); return; }
+            emit(XE_SPEC, mid, zero, zero, zero, 0u);
+            r.orig = pos; r.dir = outDir;
+        }
+    }
+}
+
+struct XShade
+{
+    V3 e[TPT_MAX_DEPTH + 1], a[TPT_MAX_DEPTH + 1];
+    int n;
+    bool doMaterialE;
+};
+TPT_HD void xshade_begin(XShade& sh) { sh.n = 0; sh.doMaterialE = true; }
+
+// Consumes one event. lightFn(mid, pos, normal, rdir, albedo, rng) returns the Lambert vertex's lightE (Test.cpp:96-133).
+// Returns true when the sample has ended: `result` is then Trace()'s return value for the camera ray.
+template <class LightFn>
+TPT_D bool xshade_event(const SceneView& sc, XShade& sh, int type, int mid, V3 a, V3 b, V3 c, uint32_t rng, LightFn&& lightFn, V3& result)
+{
+    if (type == XE_END_SKY) result = sky(a);
+    else
+    {
+        Mat mat = load_mat(sc, mid);
+        V3 matE = mat.emissive;
+        if (type == XE_END_MATE) result = matE;
+        else
+        {
+            V3 lightE = v3(0, 0, 0), attenuation;
+            if (type == XE_LAMBERT)
+            {
+                attenuation = mat.albedo;
+                lightE = lightFn(mid, a, b, c, mat.albedo, rng);
+            }
+            else attenuation = mat.type == kMetal ? mat.albedo : v3(1, 1, 1);   // Test.cpp:149 / :158
+            if (!sh.doMaterialE) matE = v3(0, 0, 0);      // Test.cpp:210
+            sh.doMaterialE = (type != XE_LAMBERT);        // Test.cpp:214
+            sh.e[sh.n] = matE + lightE;
+            sh.a[sh.n] = attenuation;
+            ++sh.n;
+            return false;
+        }
+    }
+    for (int k = sh.n - 1; k >= 0; --k) result = sh.e[k] + sh.a[k] * result;   // Test.cpp:216, back to front
+    return true;
+}
+
+// Reference-order light loop for one Lambert vertex with a hitter that traces one ray at a time (host simulation, and the
+// semantics the device's grouped version must reproduce).
+template <class Hitter>
+TPT_D V3 xlights_serial(const SceneView& sc, const Hitter& hitter, int mid, V3 pos, V3 normal, V3 rdir, V3 albedo, uint32_t rng)
+{
+    V3 lightE = v3(0, 0, 0);
+    for (int j = 0; j < sc.nLights; ++j)
+    {
+        const LightRec L = sc.lights[j];
+        if (L.id == mid) continue;
+        V3 l, contrib;
+        sample_light<true>(L, pos, normal, rdir, albedo, rng, l, contrib);
+        float ts;
+        if (hitter.hit(sc, pos, l, TPT_MIN_T, TPT_MAX_T, ts) == L.id) lightE = lightE + contrib;
+    }
+    return lightE;
+}
+
+} // namespace tpt
