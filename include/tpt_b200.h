@@ -28,6 +28,14 @@ typedef struct tpt_context tpt_context;
  *                 rays/sample. Throughput mode. */
 #define TPT_MODE_EXACT 0
 #define TPT_MODE_FAST 1
+/* TPT_MODE_REFGPU       the estimator of the reference's own GPU back-ends (Cpp/Windows/ComputeShader.hlsl:353-395 and the
+ *                       Metal port): per-PIXEL seed (x*1973 + y*9277 + frames*26699)|1, analytic disk/sphere samplers,
+ *                       saturating schlick, <= 10 path segments, lerp(col, prev, f) blend, alpha written as 1 — for like-
+ *                       for-like comparison with the reference's published D3D11/Metal numbers (readme.md:64-77). Strict
+ *                       IEEE arithmetic: bit-equal to the CPU restatement oracle/refgpu_restate.cpp.
+ * TPT_MODE_REFGPU_FAST  the same with GPU-native arithmetic (FMA, MUFU), as a real shader compiler would emit. */
+#define TPT_MODE_REFGPU 2
+#define TPT_MODE_REFGPU_FAST 3
 
 /* testFlags of Cpp/Source/Test.h:4-8 */
 #define TPT_FLAG_ANIMATE 1u
@@ -65,7 +73,10 @@ int tpt_set_spp(tpt_context* ctx, int spp);
  * copy stream waits on them with cuStreamWaitValue32, "progress_bands" bands, default 4; 0 falls back to host_bands),
  * "fast_kform" (default 1: the fast kernels may use the expanded-form sphere sweep when the scene passes the gate in
  * tpt_set_scene; per context), "fast_alpha_zero" (default 0; 1: fast-mode draws whose `prev` has zero weight write
- * alpha = 0 instead of keeping the buffer's alpha — saves the read over NVLink when the buffer is a peer GPU's). */
+ * alpha = 0 instead of keeping the buffer's alpha — saves the read over NVLink when the buffer is a peer GPU's),
+ * "mitsuba_compare" (default 0; DO_MITSUBA_COMPARE of Config.h:25 as a runtime switch, applied by the NEXT
+ * tpt_set_scene: constant sky (0.15, 0.21, 0.3) (Test.cpp:226-227) and zero Metal roughness (Test.cpp:143-145); the
+ * switch's third effect, zero aperture (Test.cpp:312-313), is camera data: the Test.h shim's UpdateTest applies it). */
 int tpt_set_option(tpt_context* ctx, const char* key, int value);
 
 /* Replaces DrawTest() (Test.cpp:344-367) for frames [frameCount, frameCount+numFrames) — numFrames*spp samples
@@ -117,7 +128,8 @@ int tpt_ipc_open(tpt_context* ctx, const void* handle64, void** outDevPtr);
 int tpt_ipc_close(tpt_context* ctx, void* devPtr);
 
 /* Diagnostic used by the parity tests: evaluates the device-side libm restatement the exact mode uses
- * (toypathtracer_b200/csrc/tpt_libm.cuh) on n host floats. fn: 0 = sinf, 1 = cosf, 2 = powf(x, 5). */
+ * (toypathtracer_b200/csrc/tpt_libm.cuh) on n host floats. fn: 0 = sinf, 1 = cosf, 2 = powf(x, 5), 3 = powf(x, 1.0f/3.0f)
+ * (the REFGPU mode's pow(x, 1.0/3.0), ComputeShader.hlsl:33). */
 int tpt_debug_libm(tpt_context* ctx, int fn, const float* in, float* out, long long n);
 /* Diagnostic: device timestamps (ms since the start of the last progress-mode host draw) of the trace kernel's end,
  * each band copy's end and the draw's end. Returns minus the number of entries written. */

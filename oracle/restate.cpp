@@ -139,6 +139,7 @@ struct Scene
     std::vector<int> emissive;                  // Test.cpp:321-338
     CameraRaw cam;
     int simdTie;                                // 1: SSE HitSpheres semantics (reference build), 0: scalar
+    int mitsuba;                                // DO_MITSUBA_COMPARE (Config.h:25) as a runtime switch
 };
 
 // Maths.cpp:50-203. Scalar loop (Maths.cpp:165-202) over simdCount spheres *including* the padded
@@ -233,6 +234,7 @@ bool Scatter(const Scene& sc, int matId, const Ray& r_in, const Hit& rec, f3& at
     {
         f3 refl = reflect(r_in.dir, rec.normal);
         float roughness = mat.roughness;
+        if (sc.mitsuba) roughness = 0;          // Test.cpp:143-145
         scattered.orig = rec.pos;
         scattered.dir = normalize(refl + roughness * RandomInUnitSphere(state));
         attenuation = ld3(mat.albedo);
@@ -322,7 +324,8 @@ f3 Trace(const Scene& sc, Ray r, long long& rayCount, uint32_t& state, long long
         }
         else
         {
-            // sky, Test.cpp:229-231
+            // sky, Test.cpp:224-232
+            if (sc.mitsuba) { result = mk(0.15f, 0.21f, 0.3f); break; }   // Test.cpp:226-227
             float t = 0.5f * (r.dir.y + 1.0f);
             result = ((1.0f - t) * mk(1.0f, 1.0f, 1.0f) + t * mk(0.5f, 0.7f, 1.0f)) * 0.3f;
             break;
@@ -385,7 +388,13 @@ void TraceRow(const Scene& sc, int y, int frameCount, int w, int h, unsigned fla
 
 } // namespace
 
+static int g_mitsuba = 0;
+
 extern "C" {
+
+// DO_MITSUBA_COMPARE for the following orc_render* calls (constant sky, zero Metal roughness; the zero aperture is camera
+// data supplied by the caller).
+void orc_set_mitsuba(int on) { g_mitsuba = on; }
 
 // spheres: count x {cx,cy,cz,radius,invRadius} (invRadius recomputed like UpdateTest, Test.cpp:325);
 // mats: count x 36 B; cam: 88 B. Renders frames [frame0, frame0+nframes) like the reference shells do
@@ -404,6 +413,7 @@ int orc_render_rows(const float* spheres, const void* mats, int count, const voi
     sc.count = count;
     sc.simdCount = (count + 3) / 4 * 4;
     sc.simdTie = simd_tie;
+    sc.mitsuba = g_mitsuba;
     sc.cx.assign(sc.simdCount, 10000.0f); sc.cy = sc.cx; sc.cz = sc.cx;
     sc.sqR.assign(sc.simdCount, 0.0f); sc.invR.assign(sc.simdCount, 0.0f);
     sc.spheres.resize(count); sc.mats.resize(count + 1);

@@ -81,4 +81,17 @@ long long check_powf_random(long long n, uint32_t seed)
     }
     return bad;
 }
+
+// powf(x, y) over the 2^24 values RandomFloat01() can return (the REFGPU mode's pow(r, 1.0/3.0), ComputeShader.hlsl:33)
+long long check_powf_rand01_domain(float y)
+{
+    long long bad = 0;
+    for (uint32_t k = 0; k < (1u << 24); ++k)
+    {
+        float x = k / 16777216.0f;
+        float a = tptlibm::powf_glibc(x, y), b = powf(x, y);
+        if (tptlibm::f2u(a) != tptlibm::f2u(b)) ++bad;
+    }
+    return bad;
+}
 }

@@ -30,3 +30,10 @@ def test_powf_x5_all_floats(host_sim):
     first = ctypes.c_ulonglong(0)
     nthreads = max(1, os.cpu_count() or 1)
     assert L.check_powf_all_x(ctypes.c_float(5.0), nthreads, ctypes.byref(first)) == 0, hex(first.value)
+
+
+def test_powf_cuberoot_whole_rand01_domain(host_sim):
+    """pow(RandomFloat01(), 1.0/3.0) of the reference's GPU sampler (ComputeShader.hlsl:33), all 2^24 arguments."""
+    L = host_sim["libm_check"]
+    L.check_powf_rand01_domain.restype = ctypes.c_longlong
+    assert L.check_powf_rand01_domain(ctypes.c_float(1.0 / 3.0)) == 0

@@ -26,6 +26,8 @@ SHIM_PATH = os.path.join(_HERE, "libtoytest_b200.so")
 
 MODE_EXACT = 0
 MODE_FAST = 1
+MODE_REFGPU = 2        # the reference's GPU-shader estimator (ComputeShader.hlsl), strict arithmetic
+MODE_REFGPU_FAST = 3   # the same with GPU-native arithmetic
 kFlagAnimate = 1      # Cpp/Source/Test.h:6
 kFlagProgressive = 2  # Cpp/Source/Test.h:7
 
@@ -258,6 +260,7 @@ def _load_shim():
     S._Z12GetSceneDescPvS_S_S_Pi.argtypes = [vp, vp, vp, vp, ctypes.POINTER(ci)]; S._Z12GetSceneDescPvS_S_S_Pi.restype = None
     S.tpt_shim_set_mode.argtypes = [ci]; S.tpt_shim_set_mode.restype = None
     S.tpt_shim_reset_scene.argtypes = []; S.tpt_shim_reset_scene.restype = None
+    S.tpt_shim_set_variant.argtypes = [ci, ci]; S.tpt_shim_set_variant.restype = None
     _shim = S
     return S
 
@@ -300,7 +303,7 @@ def GetSceneDesc():
     """Test.h:17 -> (spheres[n] SPHERE_DTYPE, materials[n] MATERIAL_DTYPE, camera CAMERA_DTYPE, emissive ids)."""
     n, so, sm, sc = GetObjectCount()
     spheres = np.zeros(n, SPHERE_DTYPE); mats = np.zeros(n, MATERIAL_DTYPE); cam = np.zeros(1, CAMERA_DTYPE)
-    em = np.zeros(n, np.int32); ec = ctypes.c_int(0)
+    em = np.zeros(max(n, 1), np.int32); ec = ctypes.c_int(0)
     _load_shim()._Z12GetSceneDescPvS_S_S_Pi(spheres.ctypes.data, mats.ctypes.data, cam.ctypes.data, em.ctypes.data,
                                             ctypes.byref(ec))
     return spheres, mats, cam, em[: ec.value].copy()
@@ -309,6 +312,12 @@ def GetSceneDesc():
 def reset_scene():
     """Un-animated scene again (UpdateTest with kFlagAnimate moves spheres 1 and 8 permanently, Test.cpp:304-308)."""
     _load_shim().tpt_shim_reset_scene()
+
+
+def set_variant(big_scene: bool = True, mitsuba_compare: bool = False):
+    """The reference's compile-time switches DO_BIG_SCENE (Test.cpp:10-11: 46 vs 9 spheres) and DO_MITSUBA_COMPARE
+    (Config.h:25: constant sky, zero Metal roughness, zero aperture) at run time; resets the scene."""
+    _load_shim().tpt_shim_set_variant(1 if big_scene else 0, 1 if mitsuba_compare else 0)
 
 
 def set_mode(mode: int):

@@ -4,9 +4,12 @@
 // Host side keeps what UpdateTest does (scene animation, camera construction, emissive list — Test.cpp:302-342);
 // DrawTest forwards to the CUDA kernels through the C-ABI (include/tpt_b200.h). No tracing happens on the CPU.
 //
-// Extra C entry points (not in Test.h) select the mode/device: tpt_shim_set_mode(), tpt_shim_context().
-// Environment: TPT_MODE=exact|fast (default exact: results bit-identical to the reference), TPT_DEVICE=<n>,
-// TPT_PIN_BACKBUFFER=1 (cudaHostRegister the caller's backbuffer once).
+// Extra C entry points (not in Test.h) select the mode/device: tpt_shim_set_mode(), tpt_shim_context(), and the
+// reference's two compile-time scene switches as runtime ones: tpt_shim_set_variant(bigScene, mitsubaCompare)
+// (DO_BIG_SCENE Test.cpp:10-11, DO_MITSUBA_COMPARE Config.h:25).
+// Environment: TPT_MODE=exact|fast|refgpu|refgpu_fast (default exact: results bit-identical to the reference),
+// TPT_DEVICE=<n>, TPT_PIN_BACKBUFFER=1 (cudaHostRegister the caller's backbuffer once), TPT_BIG_SCENE=0|1,
+// TPT_MITSUBA=0|1.
 #include "../../include/tpt_b200.h"
 #include <math.h>
 #include <stdint.h>
@@ -32,10 +35,12 @@ struct Material { int type; float albedo[3]; float emissive[3]; float roughness;
 struct Camera { float origin[3], lowerLeftCorner[3], horizontal[3], vertical[3], uu[3], vv[3], ww[3]; float lensRadius; }; // Maths.h:444-449
 enum { Lambert = 0, Metal = 1, Dielectric = 2 };
 
-const int kSphereCount = 46;
-Sphere s_Spheres[kSphereCount];
-Material s_SphereMats[kSphereCount];
-int s_EmissiveSpheres[kSphereCount];
+const int kMaxSphereCount = 46;
+int kSphereCount = 46;             // 46 spheres (2 emissive) with DO_BIG_SCENE, 9 spheres (1 emissive) without (Test.cpp:10)
+bool s_Mitsuba = false;            // DO_MITSUBA_COMPARE (Config.h:25)
+Sphere s_Spheres[kMaxSphereCount];
+Material s_SphereMats[kMaxSphereCount];
+int s_EmissiveSpheres[kMaxSphereCount];
 int s_EmissiveSphereCount;
 Camera s_Cam;
 bool s_SceneBuilt = false;
@@ -132,6 +137,14 @@ extern "C" void tpt_shim_set_mode(int mode) { s_Mode = mode; }
 // Restores the un-animated scene (the reference keeps animated positions in its static arrays forever,
 // Test.cpp:304-308; a reference shell never needs this, tests do).
 extern "C" void tpt_shim_reset_scene() { buildScene(); }
+// DO_BIG_SCENE / DO_MITSUBA_COMPARE at run time. The 9-sphere scene is the first 9 entries of the tables (Test.cpp:15-24,
+// :48-57). Takes effect with the next UpdateTest().
+extern "C" void tpt_shim_set_variant(int bigScene, int mitsubaCompare)
+{
+    kSphereCount = bigScene ? 46 : 9;
+    s_Mitsuba = mitsubaCompare != 0;
+    buildScene();
+}
 extern "C" tpt_context* tpt_shim_context() { return s_Ctx; }
 
 // Test.cpp:240-246
@@ -142,6 +155,11 @@ void InitializeTest()
     const char* m = getenv("TPT_MODE");
     if (m && !strcmp(m, "fast")) s_Mode = TPT_MODE_FAST;
     if (m && !strcmp(m, "exact")) s_Mode = TPT_MODE_EXACT;
+    if (m && !strcmp(m, "refgpu")) s_Mode = TPT_MODE_REFGPU;
+    if (m && !strcmp(m, "refgpu_fast")) s_Mode = TPT_MODE_REFGPU_FAST;
+    const char* big = getenv("TPT_BIG_SCENE");
+    const char* mit = getenv("TPT_MITSUBA");
+    if (big || mit) tpt_shim_set_variant(big ? atoi(big) : (kSphereCount == 46), mit ? atoi(mit) : (int)s_Mitsuba);
     const char* d = getenv("TPT_DEVICE");
     int rc = tpt_create(d ? atoi(d) : 0, &s_Ctx);
     if (rc) die("tpt_create", rc);
@@ -169,8 +187,8 @@ void UpdateTest(float time, int frameCount, int screenWidth, int screenHeight, u
         s_Spheres[8].center[2] = sinf(time) * 0.3f;
     }
     float distToFocus = 3;
-    float aperture = 0.1f;
-    aperture *= 0.2f; // DO_BIG_SCENE
+    float aperture = s_Mitsuba ? 0.0f : 0.1f;    // Test.cpp:311-315
+    if (kSphereCount == 46) aperture *= 0.2f;    // DO_BIG_SCENE, Test.cpp:316-318
     s_EmissiveSphereCount = 0;
     for (int i = 0; i < kSphereCount; ++i)
     {
@@ -182,6 +200,7 @@ void UpdateTest(float time, int frameCount, int screenWidth, int screenHeight, u
     buildCamera(mk(0, 2, 3), mk(0, 0, 0), mk(0, 1, 0), 60, float(screenWidth) / float(screenHeight), aperture, distToFocus);
     if (s_Ctx)
     {
+        tpt_set_option(s_Ctx, "mitsuba_compare", s_Mitsuba ? 1 : 0);
         int rc = tpt_set_scene(s_Ctx, s_Spheres, s_SphereMats, kSphereCount, &s_Cam, s_EmissiveSpheres, s_EmissiveSphereCount);
         if (rc) die("tpt_set_scene", rc);
     }

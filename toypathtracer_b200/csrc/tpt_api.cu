@@ -46,7 +46,8 @@ struct tpt_context
     // options
     int fastVariant = 3;
     int fastKForm = 1;        // expanded-form sweep allowed (still gated per scene by SceneDev::kformOk)
-    int fastAlphaZero = 0;    // 1: fast-mode draws whose `prev` has zero weight write alpha = 0 instead of preserving it
+    int fastAlphaZero = 0;
+    uint32_t sceneFlags = 0;  // kScene* bits for the next tpt_set_scene    // 1: fast-mode draws whose `prev` has zero weight write alpha = 0 instead of preserving it
     int exactLanes = 0;
     int registerHost = 0;
     size_t maxScratchBytes = (size_t)8 << 30;
@@ -240,13 +241,14 @@ int tpt_set_scene(tpt_context* ctx, const void* spheres20, const void* materials
     std::vector<unsigned char> blob;
     SceneBlobLayout L;
     int nLights = 0;
-    pack_scene_blob((const Sphere20*)spheres20, (const Material36*)materials36, count, emissives, emissiveCount, blob, L, nLights);
+    pack_scene_blob((const Sphere20*)spheres20, (const Material36*)materials36, count, emissives, emissiveCount, blob, L, nLights,
+                    ctx->sceneFlags);
     // geometry + light table must fit in shared memory next to the kernels' static shared arrays
     const uint32_t kMaxStage = 200 * 1024;
     if (L.geomBytes > kMaxStage) return fail_msg(ctx, "tpt_set_scene: too many spheres for shared-memory staging");
     // A reference shell calls UpdateTest + upload every frame although the scene only changes under kFlagAnimate
     // (Test.cpp:304-308): identical bytes are not uploaded again.
-    const bool same = ctx->haveScene && ctx->scene.count == count && blob == ctx->lastBlob;
+    const bool same = ctx->haveScene && ctx->scene.count == count && ctx->scene.layout.flags == L.flags && blob == ctx->lastBlob;
     if (!same)
     {
         const int slot = ctx->haveScene ? (ctx->curBlob ^ 1) : 0;
@@ -318,10 +320,11 @@ int tpt_set_option(tpt_context* ctx, const char* key, int value)
 {
     if (!ctx || !key) return (int)cudaErrorInvalidValue;
     if (!strcmp(key, "fast_variant")) { if (value < 0 || value > 7) return fail_msg(ctx, "fast_variant: 0..7"); ctx->fastVariant = value; return 0; }
-    if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 8 && value != 9 && value != 32 && value != 64 && value != 65) return fail_msg(ctx, "exact_lanes: 0,1,2,8,9,32,64,65"); ctx->exactLanes = value; return 0; }
+    if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 8 && value != 9 && value != 32 && (value < 64 || value > 69 || value == 68)) return fail_msg(ctx, "exact_lanes: 0,1,2,8,9,32,64..67,69"); ctx->exactLanes = value; return 0; }
     if (!strcmp(key, "register_host")) { ctx->registerHost = value ? 1 : 0; return 0; }
     if (!strcmp(key, "fast_kform")) { ctx->fastKForm = value ? 1 : 0; return 0; }
     if (!strcmp(key, "fast_alpha_zero")) { ctx->fastAlphaZero = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "mitsuba_compare")) { ctx->sceneFlags = value ? (ctx->sceneFlags | kSceneMitsuba) : (ctx->sceneFlags & ~(uint32_t)kSceneMitsuba); return 0; }
     if (!strcmp(key, "host_progress")) { ctx->hostProgress = value ? 1 : 0; return 0; }
     if (!strcmp(key, "progress_bands")) { if (value < 1 || value > 16) return fail_msg(ctx, "progress_bands: 1..16"); ctx->progressBands = value; return 0; }
     if (!strcmp(key, "host_bands")) { if (value < 1 || value > tpt_context::kMaxBands) return fail_msg(ctx, "host_bands: 1..8"); ctx->hostBands = value; return 0; }
@@ -359,7 +362,9 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
     if (!ctx->haveScene) return fail_msg(ctx, "tpt_draw: no scene (call tpt_set_scene after UpdateTest)");
     if (!backbuffer || width <= 0 || height <= 0 || numFrames <= 0 || frameCount < 0 || numRows < 0 || rowStep <= 0 || row0 < 0)
         return fail_msg(ctx, "tpt_draw: bad arguments");
-    if (mode != TPT_MODE_EXACT && mode != TPT_MODE_FAST) return fail_msg(ctx, "tpt_draw: unknown mode");
+    if (mode != TPT_MODE_EXACT && mode != TPT_MODE_FAST && mode != TPT_MODE_REFGPU && mode != TPT_MODE_REFGPU_FAST)
+        return fail_msg(ctx, "tpt_draw: unknown mode");
+    const bool refgpu = mode == TPT_MODE_REFGPU || mode == TPT_MODE_REFGPU_FAST;
     if (numRows == 0)
     {
         // an empty shard (more ranks than rows, TraceRowJob(start, start)): nothing to trace, nothing to copy
@@ -404,6 +409,7 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
         needPrev = mode == TPT_MODE_EXACT;
         if (!needPrev)
         {
+            // (REFGPU writes alpha = 1 and lerp(col, prev, 0) does not read prev: same rule as the fast mode)
             float wPrev = 1.0f;
             for (int f = 0; f < numFrames; ++f) wPrev *= lerp_fac(frameCount + f, testFlags);
             needPrev = wPrev != 0.0f;
@@ -425,6 +431,7 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
         if ((size_t)framesPerLaunch > fit) framesPerLaunch = (int)fit;
     }
     if (mode == TPT_MODE_FAST && framesPerLaunch > 256) framesPerLaunch = 256;
+
 
     if (numFrames > ctx->rayCounterCap)
     {
@@ -533,6 +540,12 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
             }
             e = launch_exact(p, scene, ctx->exactLanes, stream);
             ctx->lastLaunches += nf > 1 ? 2 : 1;
+        }
+        else if (refgpu)
+        {
+            p.rayCounter = ctx->dRayCounters;
+            e = mode == TPT_MODE_REFGPU ? launch_refgpu_exact(p, scene, ctx->numSMs, stream) : launch_refgpu_fast(p, scene, ctx->numSMs, stream);
+            ctx->lastLaunches += 1;
         }
         else
         {
@@ -709,7 +722,7 @@ int tpt_debug_timeline(tpt_context* ctx, float* outMs, int capacity)
 
 int tpt_debug_libm(tpt_context* ctx, int fn, const float* in, float* out, long long n)
 {
-    if (!ctx || !in || !out || n <= 0 || fn < 0 || fn > 2) return (int)cudaErrorInvalidValue;
+    if (!ctx || !in || !out || n <= 0 || fn < 0 || fn > 3) return (int)cudaErrorInvalidValue;
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     float *dIn = nullptr, *dOut = nullptr;
     CK(cudaMalloc(&dIn, (size_t)n * 4), "cudaMalloc");

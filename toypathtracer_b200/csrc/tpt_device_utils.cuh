@@ -79,6 +79,7 @@ __device__ __forceinline__ SceneView make_view(const unsigned char* smemBase, co
     v.count = count;
     v.simdCount = (count + 3) / 4 * 4;
     v.nLights = nLights;
+    v.flags = L.flags;
     v.sphShared = smem_u32(smemBase + L.offSph);   // geometry is always inside the staged prefix
     return v;
 }

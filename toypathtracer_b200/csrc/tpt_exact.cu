@@ -11,6 +11,7 @@
 #include "tpt_integrator.cuh"
 #include "tpt_device_utils.cuh"
 #include "tpt_launch.h"
+#include "tpt_refgpu.cuh"
 
 namespace tpt {
 
@@ -181,7 +182,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int H>
+template <int H, bool DRY = false>
 __global__ void __launch_bounds__(32 * (1 + H))
 k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights, uint32_t stagedBytes)
 {
@@ -313,6 +314,7 @@ k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneB
             if (lane == 0) mbar_arrive(&emptyBar[h][slot]);
             ++seq;
             const int tm = __float_as_int(q0.w);
+            if (DRY) { if ((tm & 3) >= XE_END_SKY) { result = v3(0, 0, 0); break; } continue; }   // probe: path warp alone
             if (xshade_event(sc, sh, tm & 3, tm >> 2, v3(q0.x, q0.y, q0.z), v3(q1.x, q1.y, q1.z), v3(q2.x, q2.y, q2.z),
                              __float_as_uint(q1.w), lights, result)) break;
         }
@@ -352,11 +354,11 @@ k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneB
     }
 }
 
-template <int H>
+template <int H, bool DRY = false>
 static cudaError_t launch_exact_split_t(const DrawParams& p, const SceneDev& sc, cudaStream_t stream)
 {
     const long long totalChains = (long long)p.numRows * p.numFrames;
-    auto kern = k_trace_exact_split<H>;
+    auto kern = k_trace_exact_split<H, DRY>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc.stagedBytes);
     if (e != cudaSuccess) return e;
     kern<<<(unsigned)totalChains, 32 * (1 + H), sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes);
@@ -381,13 +383,18 @@ __global__ void k_debug_libm(int fn, const float* __restrict__ in, float* __rest
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float x = in[i];
-    out[i] = fn == 0 ? M<true>::sin_(x) : (fn == 1 ? M<true>::cos_(x) : M<true>::pow5_(x));
+    out[i] = fn == 0 ? M<true>::sin_(x) : (fn == 1 ? M<true>::cos_(x) : (fn == 2 ? M<true>::pow5_(x) : tptlibm::powf_glibc(x, 1.0f / 3.0f)));
 }
 
 cudaError_t launch_debug_libm(int fn, const float* dIn, float* dOut, long long n, cudaStream_t stream)
 {
     k_debug_libm<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(fn, dIn, dOut, n);
     return cudaGetLastError();
+}
+
+cudaError_t launch_refgpu_exact(const DrawParams& p, const SceneDev& sc, int numSMs, cudaStream_t stream)
+{
+    return launch_refgpu_t<true>(p, sc, numSMs, stream);
 }
 
 cudaError_t launch_exact(const DrawParams& p, const SceneDev& sc, int lanes, cudaStream_t stream)
@@ -410,9 +417,11 @@ cudaError_t launch_exact(const DrawParams& p, const SceneDev& sc, int lanes, cud
     case 9: e = launch_exact_flat_t<8>(p, sc, stream); break;        // flat form with 8 lanes per chain: measured 2x SLOWER than
                                                                      // the nested form at 11 520 chains (221 vs 111 ms), comparison only
     case 32: e = launch_exact_t<32>(p, sc, stream, block); break;
-    case 64: case 65:                                                // split kernel: path warp + 1 or 2 shade warps per chain
+    case 64: case 65: case 66: case 67: case 69:                     // split kernel: path warp + 1..4 shade warps per chain
         if (p.spp > kSplitMaxSpp || totalChains > 0x7fffffffLL) return cudaErrorInvalidValue;
-        e = lanes == 64 ? launch_exact_split_t<1>(p, sc, stream) : launch_exact_split_t<2>(p, sc, stream);
+        e = lanes == 64 ? launch_exact_split_t<1>(p, sc, stream) : lanes == 65 ? launch_exact_split_t<2>(p, sc, stream)
+          : lanes == 66 ? launch_exact_split_t<3>(p, sc, stream) : lanes == 67 ? launch_exact_split_t<4>(p, sc, stream)
+          : launch_exact_split_t<2, true>(p, sc, stream);            // 69: timing probe of the path warp alone (no shading: image is NOT valid)
         break;
     default: return cudaErrorInvalidValue;
     }

@@ -15,6 +15,7 @@
 #include "tpt_device_utils.cuh"
 #include "tpt_launch.h"
 #include "tpt_fastdiv.h"
+#include "tpt_refgpu.cuh"
 
 namespace tpt {
 
@@ -211,7 +212,7 @@ k_fast_persistent(DrawParams p, const unsigned char* __restrict__ blob, SceneBlo
             {
                 if (st.kind == 0)
                 {
-                    if (id < 0) { st.col = st.col + st.thr * sky(st.d); finished = true; }
+                    if (id < 0) { st.col = st.col + st.thr * sky(st.d, sc); finished = true; }
                     else
                     {
                         Q4 s = ld_sph(sc, id);
@@ -494,7 +495,7 @@ __device__ __forceinline__ bool path_step(const SceneView& sc, QPath& st, unsign
     {
         if (st.kind == 0)
         {
-            if (id < 0) { st.col = st.col + st.thr * sky(st.d); finished = true; }
+            if (id < 0) { st.col = st.col + st.thr * sky(st.d, sc); finished = true; }
             else
             {
                 Q4 s = ld_sph(sc, id);
@@ -1019,7 +1020,7 @@ k_fast_wave(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayou
                     uint32_t rng = __float_as_uint(fthr.w);
                     const V3 d = v3(fdd.x, fdd.y, fdd.z);
                     const bool doMatE = (m2 >> 16) & 1;
-                    if (T == WT_MISS) { col = col + thr * sky(d); finished = true; }
+                    if (T == WT_MISS) { col = col + thr * sky(d, sc); finished = true; }
                     else if (T == WT_SHADOW)
                     {
                         const int j = (m2 & 0xff) - 1;
@@ -1159,6 +1160,11 @@ k_fast_wave(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayou
 #undef WFLD
     for (int off = 16; off > 0; off >>= 1) rc += __shfl_xor_sync(0xffffffffu, rc, off);
     if (lane == 0 && rc) atomicAdd(p.rayCounter, (unsigned long long)rc);
+}
+
+cudaError_t launch_refgpu_fast(const DrawParams& p, const SceneDev& sc, int numSMs, cudaStream_t stream)
+{
+    return launch_refgpu_t<false>(p, sc, numSMs, stream);
 }
 
 int fast_slab_pixels() { return kSlabPix; }

@@ -252,7 +252,7 @@ template <bool EXACT> TPT_HD float sphere_discr(const Q4 s, V3 o, V3 d, float& n
 //           update. Each lane walks ITS OWN candidates, so a warp pays max-over-lanes candidates, not the union.
 // Per sphere the arithmetic is exactly test_sphere()'s and the winner is chosen under the same total order, so
 // the result is identical to the plain loop (and to Maths.cpp:165-202 + the SSE tie rule).
-template <bool EXACT> struct SerialHitter
+template <bool EXACT, bool SSETIE = EXACT> struct SerialHitter
 {
     TPT_HD int hit(const SceneView& sc, V3 o, V3 d, float tMin, float tMax, float& tOut) const
     {
@@ -310,7 +310,7 @@ template <bool EXACT> struct SerialHitter
                     float discrSq = M<EXACT>::sqrt_(discr);
                     float t = nb - discrSq;
                     if (t <= tMin) t = nb + discrSq;
-                    if (t > tMin && hit_better<EXACT>(t, i, bestT, bestId)) { bestT = t; bestId = i; }
+                    if (t > tMin && hit_better<SSETIE>(t, i, bestT, bestId)) { bestT = t; bestId = i; }
                 }
             }
         }
@@ -450,9 +450,10 @@ TPT_HD bool scatter_specular(const Mat& mat, V3 rdir, V3 pos, V3 normal, uint32_
     return false;
 }
 
-// Sky, Test.cpp:229-231
-TPT_HD V3 sky(V3 dir)
+// Sky, Test.cpp:224-232 (DO_MITSUBA_COMPARE: constant environment, Test.cpp:226-227)
+TPT_HD V3 sky(V3 dir, const SceneView& sc)
 {
+    if (sc.flags & kSceneMitsuba) return v3(0.15f, 0.21f, 0.3f);
     float t = 0.5f * (dir.y + 1.0f);
     return ((1.0f - t) * v3(1.0f, 1.0f, 1.0f) + t * v3(0.5f, 0.7f, 1.0f)) * 0.3f;
 }
@@ -472,7 +473,7 @@ TPT_HD V3 trace_exact(const SceneView& sc, Ray r, uint32_t& state, unsigned& ray
         ++rayCount;
         float t;
         int id = hitter.hit(sc, r.orig, r.dir, TPT_MIN_T, TPT_MAX_T, t);
-        if (id < 0) { result = sky(r.dir); break; }
+        if (id < 0) { result = sky(r.dir, sc); break; }
         // Maths.cpp:156-157 / 195-196
         Q4 s = ld_sph(sc, id);
         V3 pos = r.orig + r.dir * t;
@@ -530,7 +531,7 @@ TPT_HD V3 trace_fast(const SceneView& sc, Ray r, uint32_t& state, unsigned& rayC
         ++rayCount;
         float t;
         int id = hitter.hit(sc, r.orig, r.dir, TPT_MIN_T, TPT_MAX_T, t);
-        if (id < 0) { col = col + thr * sky(r.dir); break; }
+        if (id < 0) { col = col + thr * sky(r.dir, sc); break; }
         Q4 s = ld_sph(sc, id);
         V3 pos = r.orig + r.dir * t;
         V3 normal = (pos - v3(s.x, s.y, s.z)) * sc.invRadius[id];
@@ -654,7 +655,7 @@ TPT_HD bool xchain_step(const SceneView& sc, const Camera88& cam, XChain& c, int
     int j = 0;
     if (c.kind == 0)
     {
-        if (id < 0) { result = sky(c.d); haveResult = true; }
+        if (id < 0) { result = sky(c.d, sc); haveResult = true; }
         else
         {
             Q4 s = ld_sph(sc, id);
@@ -802,7 +803,7 @@ TPT_HD void xshade_begin(XShade& sh) { sh.n = 0; sh.doMaterialE = true; }
 template <class LightFn>
 TPT_D bool xshade_event(const SceneView& sc, XShade& sh, int type, int mid, V3 a, V3 b, V3 c, uint32_t rng, LightFn&& lightFn, V3& result)
 {
-    if (type == XE_END_SKY) result = sky(a);
+    if (type == XE_END_SKY) result = sky(a, sc);
     else
     {
         Mat mat = load_mat(sc, mid);

@@ -24,6 +24,9 @@ cudaError_t launch_debug_libm(int fn, const float* dIn, float* dOut, long long n
 // form a band.
 cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, int numSMs, cudaStream_t stream,
                         unsigned int* bandDone = nullptr, int numBands = 0, unsigned int* bandExpected = nullptr);
+// TPT_MODE_REFGPU (tpt_refgpu.cuh): strict arithmetic (tpt_exact.cu) / GPU-native arithmetic (tpt_fast.cu)
+cudaError_t launch_refgpu_exact(const DrawParams& p, const SceneDev& sc, int numSMs, cudaStream_t stream);
+cudaError_t launch_refgpu_fast(const DrawParams& p, const SceneDev& sc, int numSMs, cudaStream_t stream);
 int fast_slab_pixels();
 int fast_kernel_launches(const DrawParams& p, int variant);
 

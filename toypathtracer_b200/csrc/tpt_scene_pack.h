@@ -24,13 +24,14 @@ inline SceneBlobLayout scene_blob_layout(int count, int nLights)
     L.offMatB = off;       off += align16((uint32_t)(count + 1) * 16u);
     L.offMatRi = off;      off += align16((uint32_t)(count + 1) * 4u);
     L.totalBytes = off;
+    L.flags = 0;
     return L;
 }
 
 // emissives == nullptr: derive the list like UpdateTest (Test.cpp:333-338).
 inline void pack_scene_blob(const Sphere20* spheres, const Material36* mats, int count,
                             const int* emissives, int emissiveCount,
-                            std::vector<unsigned char>& blob, SceneBlobLayout& L, int& nLights)
+                            std::vector<unsigned char>& blob, SceneBlobLayout& L, int& nLights, uint32_t sceneFlags = 0)
 {
     std::vector<int> em;
     if (emissives) em.assign(emissives, emissives + emissiveCount);
@@ -39,6 +40,7 @@ inline void pack_scene_blob(const Sphere20* spheres, const Material36* mats, int
             if (mats[i].emissive[0] > 0 || mats[i].emissive[1] > 0 || mats[i].emissive[2] > 0) em.push_back(i);
     nLights = (int)em.size();
     L = scene_blob_layout(count, nLights);
+    L.flags = sceneFlags;
     int simdCount = (count + 3) / 4 * 4;
     blob.assign(L.totalBytes, 0);
     Q4* sph = (Q4*)(blob.data() + L.offSph);
@@ -66,7 +68,8 @@ inline void pack_scene_blob(const Sphere20* spheres, const Material36* mats, int
         const Material36& m = mats[i];
         matA[i].x = m.albedo[0]; matA[i].y = m.albedo[1]; matA[i].z = m.albedo[2];
         memcpy(&matA[i].w, &m.type, 4);
-        matB[i].x = m.emissive[0]; matB[i].y = m.emissive[1]; matB[i].z = m.emissive[2]; matB[i].w = m.roughness;
+        matB[i].x = m.emissive[0]; matB[i].y = m.emissive[1]; matB[i].z = m.emissive[2];
+        matB[i].w = ((sceneFlags & kSceneMitsuba) && m.type == kMetal) ? 0.0f : m.roughness;   // Test.cpp:143-145
         matRi[i] = m.ri;
     }
     // entry [count]: all-zero (Lambert, black) — what the reference's out-of-bounds material read amounts to
@@ -93,6 +96,7 @@ inline SceneView scene_view_from_blob(const unsigned char* base, const SceneBlob
     v.count = count;
     v.simdCount = (count + 3) / 4 * 4;
     v.nLights = nLights;
+    v.flags = L.flags;
     v.sphShared = 0;
     return v;
 }

@@ -45,6 +45,7 @@ struct SceneView
     const float* matRi;
     const LightRec* lights;
     int count, simdCount, nLights;
+    uint32_t flags;       // kScene* bits
     uint32_t sphShared;   // device: 32-bit shared-memory address of sph[] (always staged), for ld.shared.v4
 };
 
@@ -55,7 +56,13 @@ struct SceneBlobLayout
 {
     uint32_t offSph, offMatA, offMatB, offLights, offInvRadius, offMatRi, totalBytes;
     uint32_t geomBytes; // bytes of [sph .. end] needed by intersection + lights only (== totalBytes here)
+    uint32_t flags;     // kScene* bits (travels to the kernels with the layout)
 };
+
+// DO_MITSUBA_COMPARE (Config.h:25) as a runtime switch: constant sky (Test.cpp:226-227) and zero Metal roughness
+// (Test.cpp:143-145; applied when the scene is packed). Its third effect, zero aperture (Test.cpp:312-313), is camera
+// data and therefore the caller's (the Test.h shim's UpdateTest builds the camera).
+enum SceneFlags : uint32_t { kSceneMitsuba = 1u };
 
 struct DrawParams
 {

@@ -33,15 +33,17 @@ def make_camera(lookfrom, lookat, vup, vfov, aspect, aperture, focus_dist) -> np
     return cam
 
 
-def reference_scene(width: int, height: int, time: float = 0.0, flags: int = 0):
+def reference_scene(width: int, height: int, time: float = 0.0, flags: int = 0, big_scene: bool = True,
+                    mitsuba_compare: bool = False):
     """(spheres, materials, camera, emissives) of the reference scene at this aspect ratio, produced by the
-    drop-in's UpdateTest + GetSceneDesc (host code only; works without a GPU)."""
-    from . import UpdateTest, GetSceneDesc, reset_scene
-    reset_scene()
+    drop-in's UpdateTest + GetSceneDesc (host code only; works without a GPU). big_scene / mitsuba_compare select the
+    reference's DO_BIG_SCENE (Test.cpp:10-11) and DO_MITSUBA_COMPARE (Config.h:25) variants; the latter only changes
+    the camera here (zero aperture) — pass Context.set_option("mitsuba_compare", 1) for its integrator effects."""
+    from . import UpdateTest, GetSceneDesc, reset_scene, set_variant
+    set_variant(big_scene, mitsuba_compare)
     UpdateTest(time, 0, width, height, flags)
     out = GetSceneDesc()
-    if flags & 1:
-        reset_scene()
+    set_variant(True, False)
     return out
 
 
