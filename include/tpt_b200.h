@@ -71,7 +71,8 @@ int tpt_set_spp(tpt_context* ctx, int spp);
  * host-buffer fast draws are split into row bands on separate streams so the D2H of one band overlaps the tracing of
  * the next), "host_progress" (default 1: with fast variant 3/4 a single kernel publishes per-band completion counters and the
  * copy stream waits on them with cuStreamWaitValue32, "progress_bands" bands, default 4; 0 falls back to host_bands),
- * "fast_kform" (default 1: the fast kernels may use the expanded-form sphere sweep when the scene passes the gate in
+ * "fast_kform" (fast kernels' sphere sweep: 0 reference form, 1 expanded form, 2 (default) expanded form evaluated two
+ * spheres per instruction with Blackwell's packed fma.rn.f32x2; 1 and 2 only when the scene passes the gate in
  * tpt_set_scene; per context), "fast_alpha_zero" (default 0; 1: fast-mode draws whose `prev` has zero weight write
  * alpha = 0 instead of keeping the buffer's alpha — saves the read over NVLink when the buffer is a peer GPU's),
  * "mitsuba_compare" (default 0; DO_MITSUBA_COMPARE of Config.h:25 as a runtime switch, applied by the NEXT

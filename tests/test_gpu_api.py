@@ -16,7 +16,7 @@ def test_fast_host_draw_touches_only_its_rows(gpu_ctx):
     must leave every other row of the caller's buffer alone — also when `prev` has zero weight and is not uploaded."""
     sph, mats, cam, em = golden_scene()
     gpu_ctx.set_scene(sph, mats, cam, em)
-    for variant in (0, 1, 3, 5):
+    for variant in (0, 1, 3, 5, 8):
         gpu_ctx.set_option("fast_variant", variant)
         for rows in [(0, 32, 1, 0), (40, 17, 1, 0), (1, 20, 7, 0)]:
             for flags in (0, 2):
@@ -42,7 +42,7 @@ def test_fast_device_buffer_keeps_alpha(gpu_ctx):
     import torch
     sph, mats, cam, em = golden_scene()
     gpu_ctx.set_scene(sph, mats, cam, em)
-    for variant in (0, 1, 3, 5, 6):
+    for variant in (0, 1, 3, 5, 6, 8):
         gpu_ctx.set_option("fast_variant", variant)
         img = torch.full((H, W, 4), float("nan"), dtype=torch.float32, device="cuda")    # prev RGB must not be read as a number
         img[..., 3] = 0.5

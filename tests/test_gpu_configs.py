@@ -213,7 +213,7 @@ def exact_16k(gpu_ctx, libs):
     return ExactPair(gpu_ctx, w, h, 4096), (sph, mats, cam, em)
 
 
-@pytest.mark.parametrize("variant,kform", [(3, 1), (3, 0), (5, 1), (5, 0)])
+@pytest.mark.parametrize("variant,kform", [(3, 2), (3, 1), (3, 0), (8, 2), (8, 0), (5, 2)])
 def test_fast_converges_to_exact_16k_spp(gpu_ctx, exact_16k, variant, kform):
     """640x360, 16 384 spp: fast (per-path streams, FMA, MUFU) vs exact (the reference's arithmetic replayed)."""
     ex, (sph, mats, cam, em) = exact_16k
@@ -224,7 +224,7 @@ def test_fast_converges_to_exact_16k_spp(gpu_ctx, exact_16k, variant, kform):
         check_fast_against_exact(gpu_ctx, ex, sph, mats, cam, 640, 360, 4096, f"640x360 v{variant} kform{kform}")
     finally:
         gpu_ctx.set_option("fast_variant", 3)
-        gpu_ctx.set_option("fast_kform", 1)
+        gpu_ctx.set_option("fast_kform", 2)
 
 
 def test_fast_converges_to_exact_720p_4k_spp(gpu_ctx, libs):

@@ -10,7 +10,7 @@ from test_oracle import golden_scene
 pytestmark = pytest.mark.gpu
 
 W, H = 640, 360
-VARIANTS = (0, 1, 3, 4, 5, 6)
+VARIANTS = (0, 1, 3, 4, 5, 6, 8)
 
 
 @pytest.fixture(scope="module")
@@ -131,14 +131,16 @@ def test_expanded_form_sweep_matches_reference_form(gpu_ctx):
     gpu_ctx.set_scene(sph, mats, cam, em)
     gpu_ctx.set_option("fast_variant", 3)
     out = []
-    for k in (1, 0):
+    for k in (2, 1, 0):
         gpu_ctx.set_option("fast_kform", k)
         img = np.zeros((H, W, 4), np.float32)
         rays = gpu_ctx.draw(0, 16, W, H, img, flags=2, mode=1)
         out.append((img, rays))
-    gpu_ctx.set_option("fast_kform", 1)
-    assert abs(out[0][1] / out[1][1] - 1) < 1e-4
-    assert rel_l2(out[0][0], out[1][0]) < 3e-3
+    gpu_ctx.set_option("fast_kform", 2)
+    # packed pairs (FFMA2) evaluate exactly the scalar expanded form's products: same candidates, same paths
+    assert out[0][1] == out[1][1] and rel_l2(out[0][0], out[1][0]) < 1e-5
+    assert abs(out[1][1] / out[2][1] - 1) < 1e-4
+    assert rel_l2(out[1][0], out[2][0]) < 3e-3
 
 
 def test_fast_odd_sizes_all_variants(gpu_ctx):
@@ -170,3 +172,40 @@ def test_more_than_256_frames_in_one_call(gpu_ctx):
     two = np.zeros((h, w, 4), np.float32)
     r2 = gpu_ctx.draw(0, 256, w, h, two, flags=2, mode=1) + gpu_ctx.draw(256, 44, w, h, two, flags=2, mode=1)
     assert r1 == r2 and rel_l2(one, two) < 1e-5
+
+
+def test_zero_copy_host_write_out(gpu_ctx):
+    """Variant 8 stores finished pixels straight into a page-locked host buffer (coalesced 128-bit stores over PCIe, no
+    staging image, no D2H copy); pageable buffers and progressive draws take the staged path. All must agree."""
+    import torch
+    sph, mats, cam, em = golden_scene()
+    gpu_ctx.set_scene(sph, mats, cam, em)
+    gpu_ctx.set_option("fast_variant", 8)
+    try:
+        ref = np.zeros((H, W, 4), np.float32)                                   # pageable: staged path
+        rays_ref = gpu_ctx.draw(7, 1, W, H, ref, flags=0, mode=1)
+        pinned = torch.full((H, W, 4), 3.0, dtype=torch.float32).pin_memory().numpy()
+        for rep in range(3):
+            pinned[...] = 3.0
+            rays = gpu_ctx.draw(7, 1, W, H, pinned, flags=0, mode=1)             # zero-copy
+            assert rays == rays_ref
+            assert rel_l2(pinned, ref) < 1e-5 and (pinned[..., 3] == 0).all()
+        gpu_ctx.set_option("host_zero_copy", 0)
+        pinned[...] = 3.0
+        assert gpu_ctx.draw(7, 1, W, H, pinned, flags=0, mode=1) == rays_ref
+        assert rel_l2(pinned, ref) < 1e-5
+        gpu_ctx.set_option("host_zero_copy", 1)
+        # a row shard of a pinned full-size buffer: only those rows are written
+        pinned[...] = 3.0
+        gpu_ctx.draw(7, 1, W, H, pinned, flags=0, mode=1, rows=(2, 50, 3, 0))
+        mine = np.zeros(H, bool); mine[2:152:3] = True
+        assert (pinned[~mine] == 3.0).all() and rel_l2(pinned[mine], ref[mine]) < 1e-5
+        # progressive (prev has weight): staged path, alpha preserved
+        pinned[...] = 0.0; pinned[..., 3] = 0.5
+        seq = np.zeros((H, W, 4), np.float32); seq[..., 3] = 0.5
+        for f in range(3):
+            gpu_ctx.draw(f, 1, W, H, pinned, flags=2, mode=1)
+            gpu_ctx.draw(f, 1, W, H, seq, flags=2, mode=1)
+        assert rel_l2(pinned, seq) < 1e-5 and (pinned[..., 3] == 0.5).all()
+    finally:
+        gpu_ctx.set_option("fast_variant", 3)

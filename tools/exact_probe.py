@@ -7,7 +7,7 @@ import toypathtracer_b200 as tpt
 
 ctx = tpt.Context(0)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); sh = stream.cuda_stream
-cases = [(1280, 720, 1, (32, 64, 65)), (3840, 2160, 1, (32, 64, 65)), (1280, 720, 16, (32, 8, 64, 65)), (1280, 720, 4, (32, 64, 65))]
+cases = [(1280, 720, 1, (32, 64, 65, 66, 67, 69)), (3840, 2160, 1, (32, 65, 66)), (1280, 720, 16, (32, 8, 66)), (1280, 720, 256, (1,))]
 if len(sys.argv) > 1:
     cases = cases[: int(sys.argv[1])]
 for (w, h, nf, lanes_list) in cases:
@@ -27,3 +27,22 @@ for (w, h, nf, lanes_list) in cases:
         rays = ctx.read_ray_count(sh)
         ms = e0.elapsed_time(e1) / reps
         print(json.dumps({"w": w, "h": h, "frames": nf, "exact_lanes": lanes, "ms": ms, "mray_s": rays / reps / ms / 1e3}), flush=True)
+
+# the reference-GPU-compatible mode (per-pixel streams): strict and native arithmetic, 720p x 4 spp, flags = 0
+w, h = 1280, 720
+ctx.set_option("exact_lanes", 0)
+ctx.set_scene(*tpt.reference_scene(w, h))
+img = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+for mode, name in ((tpt.MODE_REFGPU, "refgpu"), (tpt.MODE_REFGPU_FAST, "refgpu_fast"), (tpt.MODE_FAST, "fast")):
+    ctx.draw(0, 1, w, h, img, flags=0, mode=mode, stream=sh, want_rays=False)
+    ctx.read_ray_count(sh)
+    reps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for r in range(reps):
+        ctx.draw(1 + r, 1, w, h, img, flags=0, mode=mode, stream=sh, want_rays=False)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    rays = ctx.read_ray_count(sh)
+    ms = e0.elapsed_time(e1) / reps
+    print(json.dumps({"w": w, "h": h, "mode": name, "ms": ms, "mray_s": rays / reps / ms / 1e3}), flush=True)

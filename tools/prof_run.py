@@ -16,6 +16,8 @@ buf = ctx.mem_alloc(w * h * 16)          # device-resident image: one kernel lau
 if mode == "fast":
     ctx.set_option("fast_variant", var)
     m = tpt.MODE_FAST
+    if len(sys.argv) > 8:
+        ctx.set_option("fast_kform", int(sys.argv[8]))
 else:
     ctx.set_option("exact_lanes", var)
     m = tpt.MODE_EXACT

@@ -45,7 +45,7 @@ struct tpt_context
 
     // options
     int fastVariant = 3;
-    int fastKForm = 1;        // expanded-form sweep allowed (still gated per scene by SceneDev::kformOk)
+    int fastKForm = 2;        // 0: reference-form sweep, 1: expanded form, 2: expanded form with packed pairs (FFMA2); gated per scene by kformOk
     int fastAlphaZero = 0;
     uint32_t sceneFlags = 0;  // kScene* bits for the next tpt_set_scene    // 1: fast-mode draws whose `prev` has zero weight write alpha = 0 instead of preserving it
     int exactLanes = 0;
@@ -76,6 +76,7 @@ struct tpt_context
     typedef CUresult (*WaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
     WaitValue32Fn waitValue32 = nullptr;
     int hostProgress = 1;
+    int hostZeroCopy = 1;     // fast variant 8 stores finished pixels straight into page-locked host buffers
     int progressBands = 4;
     unsigned int* dBandDone = nullptr;
     cudaStream_t copyStream = nullptr;
@@ -319,13 +320,14 @@ int tpt_set_spp(tpt_context* ctx, int spp)
 int tpt_set_option(tpt_context* ctx, const char* key, int value)
 {
     if (!ctx || !key) return (int)cudaErrorInvalidValue;
-    if (!strcmp(key, "fast_variant")) { if (value < 0 || value > 7) return fail_msg(ctx, "fast_variant: 0..7"); ctx->fastVariant = value; return 0; }
+    if (!strcmp(key, "fast_variant")) { if (value < 0 || value > 8) return fail_msg(ctx, "fast_variant: 0..8"); ctx->fastVariant = value; return 0; }
     if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 8 && value != 9 && value != 32 && (value < 64 || value > 69 || value == 68)) return fail_msg(ctx, "exact_lanes: 0,1,2,8,9,32,64..67,69"); ctx->exactLanes = value; return 0; }
     if (!strcmp(key, "register_host")) { ctx->registerHost = value ? 1 : 0; return 0; }
-    if (!strcmp(key, "fast_kform")) { ctx->fastKForm = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "fast_kform")) { if (value < 0 || value > 2) return fail_msg(ctx, "fast_kform: 0..2"); ctx->fastKForm = value; return 0; }
     if (!strcmp(key, "fast_alpha_zero")) { ctx->fastAlphaZero = value ? 1 : 0; return 0; }
     if (!strcmp(key, "mitsuba_compare")) { ctx->sceneFlags = value ? (ctx->sceneFlags | kSceneMitsuba) : (ctx->sceneFlags & ~(uint32_t)kSceneMitsuba); return 0; }
     if (!strcmp(key, "host_progress")) { ctx->hostProgress = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "host_zero_copy")) { ctx->hostZeroCopy = value ? 1 : 0; return 0; }
     if (!strcmp(key, "progress_bands")) { if (value < 1 || value > 16) return fail_msg(ctx, "progress_bands: 1..16"); ctx->progressBands = value; return 0; }
     if (!strcmp(key, "host_bands")) { if (value < 1 || value > tpt_context::kMaxBands) return fail_msg(ctx, "host_bands: 1..8"); ctx->hostBands = value; return 0; }
     if (!strcmp(key, "max_scratch_mb")) { if (value < 16) return fail_msg(ctx, "max_scratch_mb: >= 16"); ctx->maxScratchBytes = (size_t)value << 20; return 0; }
@@ -381,27 +383,47 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
     if (ctx->haveLastDraw && ctx->lastDrawStream != stream) CK(cudaStreamWaitEvent(stream, ctx->lastDraw, 0), "order after previous draw");
     CK(cudaStreamWaitEvent(stream, ctx->uploadDone[ctx->curBlob], 0), "wait for scene upload");
     SceneDev scene = ctx->scene;
-    scene.kformOk = scene.kformOk && ctx->fastKForm;
+    scene.kformOk = scene.kformOk && ctx->fastKForm != 0;
+    scene.kformMode = ctx->fastKForm;
 
     const size_t bufRows = packed ? (size_t)numRows : (size_t)height;
     const size_t bufBytes = bufRows * width * 4 * sizeof(float);
     float* dImage = backbuffer;
     bool needPrev = true;
-    if (!bufferOnDevice)
+    bool zeroCopy = false;
+    if (!bufferOnDevice && ctx->registerHost && (ctx->registeredPtr != backbuffer || ctx->registeredBytes != bufBytes))
+    {
+        if (ctx->registeredPtr) { cudaHostUnregister(ctx->registeredPtr); ctx->registeredPtr = nullptr; }
+        // page-lock (and map) the caller's buffer once: copies run at full PCIe rate and the kernels can store into it
+        // directly; failure is not fatal
+        if (cudaHostRegister(backbuffer, bufBytes, cudaHostRegisterMapped) == cudaSuccess)
+        {
+            ctx->registeredPtr = backbuffer; ctx->registeredBytes = bufBytes;
+        }
+        else (void)cudaGetLastError();
+    }
+    if (!bufferOnDevice && mode == TPT_MODE_FAST && ctx->hostZeroCopy && fast_variant_writes_final_pixels(ctx->fastVariant))
+    {
+        // Host-buffer draw whose `prev` has zero weight, into page-locked memory the GPU can address: the trace kernel's
+        // coalesced 128-bit pixel stores go straight into the caller's buffer over PCIe while the other pixels are still
+        // being traced — no staging image, no device-to-host copy after the kernel.
+        float wPrev = 1.0f;
+        for (int f = 0; f < numFrames; ++f) wPrev *= lerp_fac(frameCount + f, testFlags);
+        cudaPointerAttributes attr;
+        if (wPrev == 0.0f && numFrames <= 256 && cudaPointerGetAttributes(&attr, backbuffer) == cudaSuccess &&
+            attr.type == cudaMemoryTypeHost && attr.devicePointer)
+        {
+            dImage = (float*)attr.devicePointer;
+            zeroCopy = true;
+            needPrev = false;
+        }
+        else (void)cudaGetLastError();
+    }
+    if (!bufferOnDevice && !zeroCopy)
     {
         int r = ensure(ctx, (void**)&ctx->dImage, &ctx->imageCap, bufBytes, "cudaMalloc image");
         if (r) return r;
         dImage = ctx->dImage;
-        if (ctx->registerHost && (ctx->registeredPtr != backbuffer || ctx->registeredBytes != bufBytes))
-        {
-            if (ctx->registeredPtr) { cudaHostUnregister(ctx->registeredPtr); ctx->registeredPtr = nullptr; }
-            // page-lock the caller's buffer once so both copies run at full PCIe rate; failure is not fatal
-            if (cudaHostRegister(backbuffer, bufBytes, cudaHostRegisterDefault) == cudaSuccess)
-            {
-                ctx->registeredPtr = backbuffer; ctx->registeredBytes = bufBytes;
-            }
-            else (void)cudaGetLastError();
-        }
         // `prev` is an input of the blend (Test.cpp:293). Exact mode always uploads it (NaN/Inf * 0 and the
         // untouched alpha are part of bit parity). Fast mode uploads it only when prev has a non-zero weight;
         // otherwise the kernel writes alpha = 0, which is what every reference shell's zero-initialised buffer
@@ -455,7 +477,7 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
     p.workCounter = ctx->dWork + (size_t)(ctx->workSlot++ % tpt_context::kWorkSlots) * 32;
     // alpha is never written by the reference (Maths.h:38). When `prev` has zero weight the fast kernels keep the alpha
     // that is in the buffer, unless the staging image was not uploaded (host buffer) or the caller waived it.
-    p.zeroAlpha = (ctx->fastAlphaZero || (!bufferOnDevice && !needPrev)) ? 1 : 0;
+    p.zeroAlpha = (ctx->fastAlphaZero || (!bufferOnDevice && !needPrev)) ? 1 : 0;     // (zero-copy: never reads host memory)
 
     ctx->lastLaunches = 0;
     CK(cudaEventRecord(ctx->evStart, stream), "event record");
@@ -561,7 +583,7 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
     CK(cudaGetLastError(), "accumulate launch");
     ctx->lastLaunches += 1;
 
-    if (!bufferOnDevice && !pipelined)
+    if (!bufferOnDevice && !pipelined && !zeroCopy)
     {
         // only the rows this draw rendered go back: the caller's other rows are not ours to touch (TraceRowJob writes
         // rows [start,end) only, Test.cpp:278-297)

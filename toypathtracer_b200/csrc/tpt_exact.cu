@@ -182,8 +182,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+constexpr int split_block_threads(int H) { return H <= 3 ? 128 : 32 * (1 + H); }   // 4-warp CTAs: one role per SM sub-partition
+
 template <int H, bool DRY = false>
-__global__ void __launch_bounds__(32 * (1 + H))
+__global__ void __launch_bounds__(split_block_threads(H))
 k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights, uint32_t stagedBytes)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -233,7 +235,7 @@ k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneB
 #pragma unroll
                                  for (int hh = 0; hh < H; ++hh) if (hh == h) sq = seq[hh];
                                  const uint32_t slot = sq % kRingDepth, phase = (sq / kRingDepth) & 1u;
-                                 mbar_wait(&emptyBar[h][slot], phase ^ 1u);      // slot free (passes at once on a fresh barrier)
+                                 mbar_wait_sleep(&emptyBar[h][slot], phase ^ 1u);      // slot free (passes at once on a fresh barrier)
                                  if (lane == 0)
                                  {
                                      XEventSlot& e = ring[h][slot];
@@ -252,6 +254,7 @@ k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneB
 
     // ---- SHADE warp h: samples k = h, h + H, ...
     const int h = warp - 1;
+    if (h >= H) return;                                          // padding warp of the 4-warp CTA
     const int grp = lane >> 4;                                   // half-warp = one light
     GroupHitter<true, 16> hitter;
     hitter.sub = lane & 15; hitter.mask = 0xffffu << (grp * 16);
@@ -307,7 +310,7 @@ k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneB
         for (;;)
         {
             const uint32_t slot = seq % kRingDepth, phase = (seq / kRingDepth) & 1u;
-            mbar_wait(&fullBar[h][slot], phase);
+            mbar_wait_sleep(&fullBar[h][slot], phase);
             const XEventSlot& e = ring[h][slot];
             const float4 q0 = e.q0, q1 = e.q1, q2 = e.q2;
             __syncwarp();
@@ -361,7 +364,7 @@ static cudaError_t launch_exact_split_t(const DrawParams& p, const SceneDev& sc,
     auto kern = k_trace_exact_split<H, DRY>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc.stagedBytes);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)totalChains, 32 * (1 + H), sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes);
+    kern<<<(unsigned)totalChains, split_block_threads(H), sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes);
     return cudaGetLastError();
 }
 

@@ -477,6 +477,112 @@ __device__ __forceinline__ void build_sphK(const SceneView& sc, float4* sphInSme
     }
 }
 
+// Packed-pair form of the expanded sweep: Blackwell's fma.rn.f32x2 / add.rn.f32x2 (SASS FFMA2 / FADD2) evaluate TWO spheres
+// per instruction, with the ray constants as scalar broadcast operands. The kernels are FP32-issue bound (ncu: issue slots
+// 78 % busy, FMA pipe 42 %), so halving the issue slots of pass 1 is worth more than its FLOPs: per PAIR of spheres
+//   2 LDS.128 {x0,x1,y0,y1} {z0,z1,-K0,-K1},  1 FADD2 (-K - o.o),  3 FFMA2 (nb),  3 FFMA2 (-c),  1 FFMA2 (discr),
+//   2 LOP3 + 2 SHF (sign bits into the candidate mask)           = 7 issue slots per sphere instead of 12.5.
+// -c and discr are the exact negations/equals of FastHitterK's c and discr (same products, IEEE negation symmetry), so pass
+// 2 — unchanged, on the {s, K} array — sees the same candidates it would have computed itself.
+__device__ __forceinline__ unsigned long long f2_bcast(float x) { unsigned long long r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(x)); return r; }
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b)
+{
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+struct FastHitterK2
+{
+    uint32_t sphK;      // shared-memory address of {sx, sy, sz, K}[simdCount]         (pass 2)
+    uint32_t sphP;      // shared-memory address of the pair array, 32 B per pair       (pass 1)
+    int simdCount;
+    __device__ __forceinline__ float4 ld(int i) const
+    {
+        float4 r;
+        asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(sphK + (uint32_t)i * 16u));
+        return r;
+    }
+    __device__ __forceinline__ void ldp(int pair, unsigned long long& xx, unsigned long long& yy, unsigned long long& zz, unsigned long long& kk) const
+    {
+        asm("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(xx), "=l"(yy) : "r"(sphP + (uint32_t)pair * 32u));
+        asm("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(zz), "=l"(kk) : "r"(sphP + (uint32_t)pair * 32u + 16u));
+    }
+    __device__ __forceinline__ int hit(const SceneView&, V3 o, V3 d, float tMin, float tMax, float& tOut) const
+    {
+        const float nod = -fmaf(o.x, d.x, fmaf(o.y, d.y, o.z * d.z));
+        const float oo = fmaf(o.x, o.x, fmaf(o.y, o.y, o.z * o.z));
+        const float ax = -2.0f * o.x, ay = -2.0f * o.y, az = -2.0f * o.z;
+        const unsigned long long DX = f2_bcast(d.x), DY = f2_bcast(d.y), DZ = f2_bcast(d.z), NOD = f2_bcast(nod);
+        const unsigned long long BX = f2_bcast(-ax), BY = f2_bcast(-ay), BZ = f2_bcast(-az), NOO = f2_bcast(-oo);
+        float bestT = tMax;
+        int bestId = -1;
+        for (int base = 0; base < simdCount; base += 32)
+        {
+            const int n = simdCount - base < 32 ? simdCount - base : 32;     // multiple of 4
+            uint32_t neg = 0;
+#pragma unroll
+            for (int k = 0; k < 32; k += 4)
+            {
+                if (k < n)
+                {
+#pragma unroll
+                    for (int j = 0; j < 4; j += 2)
+                    {
+                        unsigned long long xx, yy, zz, kk;
+                        ldp((base + k + j) >> 1, xx, yy, zz, kk);
+                        const unsigned long long nb = f2_fma(xx, DX, f2_fma(yy, DY, f2_fma(zz, DZ, NOD)));
+                        const unsigned long long negc = f2_fma(xx, BX, f2_fma(yy, BY, f2_fma(zz, BZ, f2_add(kk, NOO))));
+                        const unsigned long long discr = f2_fma(nb, nb, negc);
+                        // reject: discr < 0, or centre behind (nb < 0) with the origin outside (-c < 0)
+                        const uint32_t r0 = (uint32_t)discr | ((uint32_t)nb & (uint32_t)negc);
+                        const uint32_t r1 = (uint32_t)(discr >> 32) | ((uint32_t)(nb >> 32) & (uint32_t)(negc >> 32));
+                        neg = __funnelshift_l(r0, neg, 1);
+                        neg = __funnelshift_l(r1, neg, 1);
+                    }
+                }
+            }
+            uint32_t cand = ~neg & (n == 32 ? 0xffffffffu : ((1u << n) - 1u));
+            while (cand)
+            {
+                const int bit = 31 - __clz((int)cand);
+                cand &= ~(1u << bit);
+                const int i = base + (n - 1 - bit);
+                const float4 s = ld(i);
+                const float nb = fmaf(s.x, d.x, fmaf(s.y, d.y, fmaf(s.z, d.z, nod)));
+                const float c = fmaf(s.x, ax, fmaf(s.y, ay, fmaf(s.z, az, s.w + oo)));
+                const float discr = fmaf(nb, nb, -c);
+                if (discr > 0.0f)
+                {
+                    const float sq = M<false>::sqrt_(discr);
+                    float t = nb - sq;
+                    if (t <= tMin) t = nb + sq;
+                    if (t > tMin && t < bestT) { bestT = t; bestId = i; }
+                }
+            }
+        }
+        tOut = bestT;
+        return bestId;
+    }
+};
+
+// Pair array for FastHitterK2 from the {s, K} array build_sphK() left in place: pair p = spheres 2p, 2p+1 as
+// {x0, x1, y0, y1} {z0, z1, -K0, -K1}.
+__device__ __forceinline__ void build_sph_pairs(const SceneView& sc, const float4* sphK, float4* pairs)
+{
+    for (int p = threadIdx.x; 2 * p < sc.simdCount; p += blockDim.x)
+    {
+        const float4 a = sphK[2 * p], b = sphK[2 * p + 1];
+        pairs[2 * p] = make_float4(a.x, b.x, a.y, b.y);
+        pairs[2 * p + 1] = make_float4(a.z, b.z, -a.w, -b.w);
+    }
+}
+
 // One iteration of the per-lane path state machine shared by the queue kernels: intersect the lane's current ray
 // (path or shadow) against all spheres, then shade. Returns true when the lane's path has ended (st.col is final).
 template <class Hitter>
@@ -600,7 +706,7 @@ __device__ __forceinline__ bool path_step(const SceneView& sc, QPath& st, unsign
     return finished;
 }
 
-template <int MINB, bool KFORM>
+template <int MINB, int KFORM>     // KFORM 0: reference-form sweep, 1: expanded form, 2: expanded form, packed pairs (FFMA2)
 __global__ void __launch_bounds__(kQueueThreads, MINB)
 k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights,
              uint32_t stagedBytes, uint32_t numSlabs, uint32_t S, unsigned int* __restrict__ bandDone, uint32_t mtilesPerBand)
@@ -617,10 +723,13 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
     float4* sphK = reinterpret_cast<float4*>(smem + L.offSph);
     if (KFORM) build_sphK(sc, sphK);
     __syncthreads();
+    float4* pairs = reinterpret_cast<float4*>(smem + ((stagedBytes + 127u) & ~127u));     // KFORM 2: behind the staged blob
+    if (KFORM == 2) { build_sph_pairs(sc, sphK, pairs); __syncthreads(); }
     FastHitterK hitK; hitK.sphK = sc.sphShared; hitK.simdCount = sc.simdCount;
+    FastHitterK2 hitK2; hitK2.sphK = sc.sphShared; hitK2.sphP = smem_u32(pairs); hitK2.simdCount = sc.simdCount;
     // the sweep's loads are plain (schedulable) asm: make their address opaque AFTER the barrier so that none of them can
     // be hoisted above the in-place {s, r^2} -> {s, K} rewrite
-    asm volatile("" : "+r"(hitK.sphK));
+    asm volatile("" : "+r"(hitK.sphK), "+r"(hitK2.sphK), "+r"(hitK2.sphP));
     SerialHitter<false> hitS;
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
@@ -700,7 +809,7 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
         }
         if (!__any_sync(0xffffffffu, st.active)) break;
 
-        const bool finished = KFORM ? path_step(sc, st, rc, hitK) : path_step(sc, st, rc, hitS);
+        const bool finished = KFORM == 2 ? path_step(sc, st, rc, hitK2) : (KFORM == 1 ? path_step(sc, st, rc, hitK) : path_step(sc, st, rc, hitS));
         if (finished)
         {
             red_add_f4(p.image + (size_t)st.pixOff * 4, st.col.x * st.weight, st.col.y * st.weight, st.col.z * st.weight);
@@ -721,6 +830,164 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
     if (lane == 0 && rc) atomicAdd(p.rayCounter, (unsigned long long)rc);
 }
 
+// ---- variant 8 ------------------------------------------------------------------------------------------------
+// "warp-owned pixel groups": the warp-level dealing and path state machine of variant 3, but the unit a warp pulls from
+// the global counter is a GROUP of kGroupPix consecutive pixels with ALL their samples of this draw. The group's radiance
+// is accumulated in the warp's own shared-memory slot; when its last path ends, 16 lanes write the 16 finished float4
+// pixels with ONE coalesced 128-bit store each (256 contiguous bytes) — straight into the caller's buffer: local HBM,
+// a peer GPU's HBM over NVLink (multi-GPU write-out), or page-locked HOST memory over PCIe (host-buffer draws finish
+// with the kernel: no staging image, no device-to-host copy). No prepare kernel, no L2 reductions, no block barriers
+// after the prologue. Because of ray regeneration a warp has paths of several groups in flight: kGroupOpen slots per
+// warp; a new group is only opened in a slot whose previous group has been written out.
+constexpr int kGroupPix = 16;
+constexpr int kGroupOpen = 8;
+
+// Camera rays of one chunk of a group: `ns` sample indices [s0, s0+ns) x npix pixels, entry q = sl*npix + px, into the warp's
+// shared buffer: {origin.xyz, rng} {direction.xyz, px | slot << 4 | frame-in-draw << 8}.
+__device__ __forceinline__ void generate_group_rays(const DrawParams& p, float4 (*rays)[2], int lane, uint32_t npix, uint32_t ns,
+                                                    uint32_t pix0, uint32_t s0, uint32_t slot)
+{
+    for (uint32_t q = (uint32_t)lane; q < npix * ns; q += 32)
+    {
+        const uint32_t sl = npix == (uint32_t)kGroupPix ? q >> 4 : q / npix;
+        const uint32_t px = q - sl * npix;
+        const uint32_t gp = pix0 + px;
+        const int ri = (int)(gp / (uint32_t)p.width), x = (int)(gp - (uint32_t)ri * (uint32_t)p.width);
+        const int y = p.row0 + ri * p.rowStep;
+        const uint32_t s = s0 + sl, fi = s / (uint32_t)p.spp, ss = s - fi * (uint32_t)p.spp;
+        uint32_t rng = pixel_seed((uint32_t)(y * p.width + x) * (uint32_t)p.spp + ss, (uint32_t)p.frame0 + fi);
+        float u = ((float)x + RandomFloat01(rng)) * p.invWidth;
+        float v = ((float)y + RandomFloat01(rng)) * p.invHeight;
+        Ray r = GetRay<false>(p.cam, u, v, rng);
+        rays[q][0] = make_float4(r.orig.x, r.orig.y, r.orig.z, __uint_as_float(rng));
+        rays[q][1] = make_float4(r.dir.x, r.dir.y, r.dir.z, __uint_as_float(px | (slot << 4) | (fi << 8)));
+    }
+}
+
+template <int MINB, int KFORM>
+__global__ void __launch_bounds__(kQueueThreads, MINB)
+k_fast_group(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights,
+             uint32_t stagedBytes, uint32_t numGroups, uint32_t S, float wPrev)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ float sW[kMaxFramesPerDraw];
+    __shared__ float4 sRays[kQueueThreads / 32][kSlabPix][2];
+    __shared__ float4 sAcc[kQueueThreads / 32][kGroupOpen][kGroupPix];
+    __shared__ int sRemain[kQueueThreads / 32][kGroupOpen];
+    __shared__ uint32_t sGrpPix0[kQueueThreads / 32][kGroupOpen];
+    stage_blob(smem, blob, stagedBytes, &bar);
+    if (threadIdx.x == 0) { float wp; blend_weights(p, sW, wp); }
+    for (int i = threadIdx.x; i < (kQueueThreads / 32) * kGroupOpen * kGroupPix; i += kQueueThreads) (&sAcc[0][0][0])[i] = make_float4(0, 0, 0, 0);
+    if (threadIdx.x < (kQueueThreads / 32) * kGroupOpen) (&sRemain[0][0])[threadIdx.x] = 0;
+    SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
+    float4* sphK = reinterpret_cast<float4*>(smem + L.offSph);
+    if (KFORM) build_sphK(sc, sphK);
+    __syncthreads();
+    float4* pairs = reinterpret_cast<float4*>(smem + ((stagedBytes + 127u) & ~127u));
+    if (KFORM == 2) { build_sph_pairs(sc, sphK, pairs); __syncthreads(); }
+    FastHitterK hitK; hitK.sphK = sc.sphShared; hitK.simdCount = sc.simdCount;
+    FastHitterK2 hitK2; hitK2.sphK = sc.sphShared; hitK2.sphP = smem_u32(pairs); hitK2.simdCount = sc.simdCount;
+    asm volatile("" : "+r"(hitK.sphK), "+r"(hitK2.sphK), "+r"(hitK2.sphP));     // see k_fast_queue
+    SerialHitter<false> hitS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const uint32_t regionPix = (uint32_t)((long long)p.numRows * p.width);
+    const float invSpp = 1.0f / (float)p.spp;
+    unsigned rc = 0;
+
+    // warp-uniform cursors: current chunk of rays in sRays, current group
+    uint32_t chunkCur = 0, chunkEnd = 0;
+    uint32_t sNext = S;                     // next sample index of the current group to generate (== S: group exhausted)
+    uint32_t grpPix0 = 0, grpNpix = 0, curSlot = 0, groupsOpened = 0;
+    bool exhausted = false;
+
+    QPath st;
+    st.active = false;
+    for (;;)
+    {
+        // ---- regeneration
+        unsigned need = __ballot_sync(0xffffffffu, !st.active);
+        while (need && !exhausted)
+        {
+            if (chunkCur >= chunkEnd)
+            {
+                if (sNext >= S)
+                {
+                    const uint32_t slot = groupsOpened % (uint32_t)kGroupOpen;
+                    if (sRemain[warp][slot] != 0) break;        // that slot's group still has paths in flight: trace them first
+                    uint32_t g = 0;
+                    if (lane == 0) g = atomicAdd(p.workCounter, 1u);
+                    g = __shfl_sync(0xffffffffu, g, 0);
+                    if (g >= numGroups) { exhausted = true; break; }
+                    grpPix0 = g * (uint32_t)kGroupPix;
+                    grpNpix = regionPix - grpPix0 < (uint32_t)kGroupPix ? regionPix - grpPix0 : (uint32_t)kGroupPix;
+                    curSlot = slot; ++groupsOpened; sNext = 0;
+                    if (lane == 0) { sRemain[warp][slot] = (int)(grpNpix * S); sGrpPix0[warp][slot] = grpPix0; }
+                }
+                const uint32_t ns = S - sNext < 4u ? S - sNext : 4u;
+                __syncwarp();       // every lane has popped what it needed from the previous chunk
+                generate_group_rays(p, sRays[warp], lane, grpNpix, ns, grpPix0, sNext, curSlot);
+                __syncwarp();
+                chunkCur = 0; chunkEnd = grpNpix * ns; sNext += ns;
+            }
+            const uint32_t avail = chunkEnd - chunkCur;
+            const uint32_t rank = (uint32_t)__popc(need & ltMask);
+            if (!st.active && rank < avail)
+            {
+                const float4 e0 = sRays[warp][chunkCur + rank][0];
+                const float4 e1 = sRays[warp][chunkCur + rank][1];
+                st.o = v3(e0.x, e0.y, e0.z); st.d = v3(e1.x, e1.y, e1.z);
+                st.rng = __float_as_uint(e0.w);
+                const uint32_t tag = __float_as_uint(e1.w);
+                st.pixOff = tag & 0xffu;                         // px | slot << 4
+                st.weight = invSpp * sW[tag >> 8];
+                st.thr = v3(1, 1, 1); st.col = v3(0, 0, 0);
+                st.kind = 0; st.depth = 0; st.doMaterialE = true; st.active = true;
+            }
+            const uint32_t n = (uint32_t)__popc(need);
+            chunkCur += n < avail ? n : avail;
+            need = __ballot_sync(0xffffffffu, !st.active);
+        }
+        if (!__any_sync(0xffffffffu, st.active)) break;
+
+        const bool finished = KFORM == 2 ? path_step(sc, st, rc, hitK2) : (KFORM == 1 ? path_step(sc, st, rc, hitK) : path_step(sc, st, rc, hitS));
+        bool lastOfGroup = false;
+        if (finished)
+        {
+            float* a = reinterpret_cast<float*>(&sAcc[warp][st.pixOff >> 4][st.pixOff & 15u]);
+            atomicAdd(a + 0, st.col.x * st.weight);
+            atomicAdd(a + 1, st.col.y * st.weight);
+            atomicAdd(a + 2, st.col.z * st.weight);
+            st.active = false;
+            lastOfGroup = atomicSub(&sRemain[warp][st.pixOff >> 4], 1) == 1;
+        }
+        // ---- a group completed: 16 lanes write its 16 pixels, one coalesced 128-bit store each
+        unsigned trig = __ballot_sync(0xffffffffu, lastOfGroup);
+        while (trig)
+        {
+            const int src = __ffs(trig) - 1;
+            trig &= trig - 1;
+            const uint32_t slot = __shfl_sync(0xffffffffu, st.pixOff >> 4, src);
+            const uint32_t pix0 = sGrpPix0[warp][slot];
+            const uint32_t npix = regionPix - pix0 < (uint32_t)kGroupPix ? regionPix - pix0 : (uint32_t)kGroupPix;
+            if ((uint32_t)lane < npix)
+            {
+                const uint32_t gp = pix0 + (uint32_t)lane;
+                const int ri = (int)(gp / (uint32_t)p.width), x = (int)(gp - (uint32_t)ri * (uint32_t)p.width);
+                const int y = p.row0 + ri * p.rowStep;
+                float* px = p.image + ((size_t)(p.packed ? ri : y) * p.width + x) * 4;
+                const float4 a = sAcc[warp][slot][lane];
+                st_stream_f4(px, blend_prev(p, px, wPrev, a.x, a.y, a.z));
+                sAcc[warp][slot][lane] = make_float4(0, 0, 0, 0);
+            }
+            __syncwarp();
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) rc += __shfl_xor_sync(0xffffffffu, rc, off);
+    if (lane == 0 && rc) atomicAdd(p.rayCounter, (unsigned long long)rc);
+}
+
 // ---- variant 5 ------------------------------------------------------------------------------------------------
 // "tile queue": the warp-level slab dealing and path state machine of variant 3, but a CTA owns a tile of kTileQPix
 // pixels for ALL its samples: radiance is accumulated in shared memory and the finished tile is written ONCE with
@@ -730,7 +997,7 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
 // S = spp x frames >= 16 the per-tile tail is < 1 %, at S = 4 variant 3 is the better choice.
 constexpr int kTileQPix = 1024;
 
-template <int MINB, bool KFORM>
+template <int MINB, int KFORM>
 __global__ void __launch_bounds__(kQueueThreads, MINB)
 k_fast_tileq(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights,
              uint32_t stagedBytes, uint32_t numTiles, uint32_t S, float wPrev, uint32_t tileQPix)
@@ -748,8 +1015,11 @@ k_fast_tileq(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
     float4* sphK = reinterpret_cast<float4*>(smem + L.offSph);
     if (KFORM) build_sphK(sc, sphK);
     __syncthreads();
+    float4* pairs = reinterpret_cast<float4*>(smem + ((stagedBytes + 127u) & ~127u));
+    if (KFORM == 2) { build_sph_pairs(sc, sphK, pairs); __syncthreads(); }
     FastHitterK hitK; hitK.sphK = sc.sphShared; hitK.simdCount = sc.simdCount;
-    asm volatile("" : "+r"(hitK.sphK));     // see k_fast_queue
+    FastHitterK2 hitK2; hitK2.sphK = sc.sphShared; hitK2.sphP = smem_u32(pairs); hitK2.simdCount = sc.simdCount;
+    asm volatile("" : "+r"(hitK.sphK), "+r"(hitK2.sphK), "+r"(hitK2.sphP));     // see k_fast_queue
     SerialHitter<false> hitS;
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
@@ -820,7 +1090,7 @@ k_fast_tileq(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
                 need = __ballot_sync(0xffffffffu, !st.active);
             }
             if (!__any_sync(0xffffffffu, st.active)) break;
-            if (KFORM ? path_step(sc, st, rc, hitK) : path_step(sc, st, rc, hitS))
+            if (KFORM == 2 ? path_step(sc, st, rc, hitK2) : (KFORM == 1 ? path_step(sc, st, rc, hitK) : path_step(sc, st, rc, hitS)))
             {
                 atomicAdd(&sAcc[st.pixOff * 3 + 0], st.col.x * st.weight);
                 atomicAdd(&sAcc[st.pixOff * 3 + 1], st.col.y * st.weight);
@@ -1170,6 +1440,7 @@ cudaError_t launch_refgpu_fast(const DrawParams& p, const SceneDev& sc, int numS
 int fast_slab_pixels() { return kSlabPix; }
 
 int fast_kernel_launches(const DrawParams&, int variant) { return (variant == 3 || variant == 4 || variant == 6 || variant == 7) ? 2 : 1; }
+bool fast_variant_writes_final_pixels(int variant) { return variant == 8; }
 
 
 
@@ -1207,9 +1478,13 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
     if (variant == 3 || variant == 4)
     {
         // expanded-form sweep (8 FP32 slots/test): K replaces r^2 in the staged sphere array
-        const bool kform = sc.kformOk;
-        auto kern = variant == 3 ? (kform ? k_fast_queue<TPT_QUEUE_MINB, true> : k_fast_queue<TPT_QUEUE_MINB, false>) : (kform ? k_fast_queue<8, true> : k_fast_queue<8, false>);
-        const size_t dyn3 = sc.stagedBytes;
+        // sweep form: 2 = expanded + packed pairs (FFMA2; the pair array costs 16 B per sphere of extra shared memory),
+        // 1 = expanded, 0 = reference form
+        const int simd = (sc.count + 3) / 4 * 4;
+        const int kform = !sc.kformOk ? 0 : (sc.kformMode == 1 || simd > 1024 ? 1 : 2);
+        auto kern = variant == 3 ? (kform == 2 ? k_fast_queue<TPT_QUEUE_MINB, 2> : kform == 1 ? k_fast_queue<TPT_QUEUE_MINB, 1> : k_fast_queue<TPT_QUEUE_MINB, 0>)
+                                 : (kform == 2 ? k_fast_queue<8, 2> : kform == 1 ? k_fast_queue<8, 1> : k_fast_queue<8, 0>);
+        const size_t dyn3 = kform == 2 ? ((sc.stagedBytes + 127u) & ~127u) + (size_t)simd * 16 : sc.stagedBytes;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn3);
         if (e != cudaSuccess) return e;
         int perSM = 0;
@@ -1247,6 +1522,33 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
                                                                 (uint32_t)slabs, S, mpb ? bandDone : nullptr, mpb ? mpb : 1u);
         return cudaGetLastError();
     }
+    if (variant == 8)
+    {
+        const int simd = (sc.count + 3) / 4 * 4;
+        const int kform = !sc.kformOk ? 0 : (sc.kformMode == 1 || simd > 1024 ? 1 : 2);
+        auto kern = kform == 2 ? k_fast_group<TPT_QUEUE_MINB, 2> : kform == 1 ? k_fast_group<TPT_QUEUE_MINB, 1> : k_fast_group<TPT_QUEUE_MINB, 0>;
+        const size_t dyn8 = kform == 2 ? ((sc.stagedBytes + 127u) & ~127u) + (size_t)simd * 16 : sc.stagedBytes;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn8);
+        if (e != cudaSuccess) return e;
+        int perSM = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kQueueThreads, dyn8);
+        if (e != cudaSuccess) return e;
+        if (perSM < 1) perSM = 1;
+        float wPrev = 1.0f;
+        for (int f = 0; f < p.numFrames; ++f) wPrev *= lerp_fac(p.frame0 + f, p.flags);
+        const long long regionPix = (long long)p.numRows * p.width;
+        const uint32_t S = (uint32_t)(p.spp * p.numFrames);
+        const long long groups = (regionPix + kGroupPix - 1) / kGroupPix;
+        if (groups > 0x7fffffffLL) return cudaErrorInvalidValue;
+        long long grid = (long long)numSMs * perSM;
+        const long long ctasNeeded = (groups + kQueueThreads / 32 - 1) / (kQueueThreads / 32);
+        if (grid > ctasNeeded) grid = ctasNeeded;
+        e = cudaMemsetAsync(p.workCounter, 0, sizeof(unsigned int), stream);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)grid, kQueueThreads, dyn8, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes,
+                                                                (uint32_t)groups, S, wPrev);
+        return cudaGetLastError();
+    }
     if (variant == 6 || variant == 7)
     {
         auto kern = variant == 6 ? k_fast_wave<3> : k_fast_wave<4>;
@@ -1280,9 +1582,10 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
     }
     if (variant == 5)
     {
-        const bool kform = sc.kformOk;
-        auto kern = kform ? k_fast_tileq<6, true> : k_fast_tileq<6, false>;
-        const size_t dyn5 = sc.stagedBytes;
+        const int simd = (sc.count + 3) / 4 * 4;
+        const int kform = !sc.kformOk ? 0 : (sc.kformMode == 1 || simd > 1024 ? 1 : 2);
+        auto kern = kform == 2 ? k_fast_tileq<6, 2> : kform == 1 ? k_fast_tileq<6, 1> : k_fast_tileq<6, 0>;
+        const size_t dyn5 = kform == 2 ? ((sc.stagedBytes + 127u) & ~127u) + (size_t)simd * 16 : sc.stagedBytes;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn5);
         if (e != cudaSuccess) return e;
         int perSM = 0;

@@ -44,13 +44,30 @@ TPT_HD float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 TPT_HD V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 TPT_HD V3 ld3(const float* p) { return v3(p[0], p[1], p[2]); }
 
+// The glibc restatements are a few hundred instructions each. They are called, not inlined: the exact kernels are
+// latency-bound chains whose code has to stay inside the instruction cache (the split kernel ran at a 79 % i-cache hit
+// rate with everything inlined), and a call costs a handful of cycles next to ~150 dependent double-precision operations.
+#if defined(__CUDACC__)
+#define TPT_OUTLINE static __host__ __device__ __noinline__
+#else
+#define TPT_OUTLINE static inline
+#endif
+TPT_OUTLINE float exact_sinf(float a) { float r; if (tptlibm::sinf_glibc(a, &r)) return r; return sinf(a); }
+TPT_OUTLINE float exact_cosf(float a) { float r; if (tptlibm::cosf_glibc(a, &r)) return r; return cosf(a); }
+TPT_OUTLINE float exact_pow5f(float x) { return tptlibm::powf_glibc(x, 5.0f); }
+#if defined(__CUDA_ARCH__)
+// IEEE sqrt / division expand to ~15 instructions + a slow-path call at every use: one shared copy each
+TPT_OUTLINE float exact_sqrtf(float x) { return __fsqrt_rn(x); }
+TPT_OUTLINE float exact_divf(float a, float b) { return __fdiv_rn(a, b); }
+#endif
+
 template <bool EXACT> struct M
 {
     // IEEE-exact in EXACT mode; approximate reciprocal / rsqrt forms allowed otherwise.
     static TPT_HD float sqrt_(float x)
     {
 #if defined(__CUDA_ARCH__)
-        if (EXACT) return __fsqrt_rn(x);
+        if (EXACT) return exact_sqrtf(x);
         float r;
         asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
         return r;
@@ -61,14 +78,14 @@ template <bool EXACT> struct M
     static TPT_HD float div_(float a, float b)
     {
 #if defined(__CUDA_ARCH__)
-        return EXACT ? __fdiv_rn(a, b) : __fdividef(a, b);
+        return EXACT ? exact_divf(a, b) : __fdividef(a, b);
 #else
         return a / b;
 #endif
     }
     static TPT_HD float sin_(float a)
     {
-        if (EXACT) { float r; if (tptlibm::sinf_glibc(a, &r)) return r; return sinf(a); }
+        if (EXACT) return exact_sinf(a);
 #if defined(__CUDA_ARCH__)
         return __sinf(a);
 #else
@@ -77,7 +94,7 @@ template <bool EXACT> struct M
     }
     static TPT_HD float cos_(float a)
     {
-        if (EXACT) { float r; if (tptlibm::cosf_glibc(a, &r)) return r; return cosf(a); }
+        if (EXACT) return exact_cosf(a);
 #if defined(__CUDA_ARCH__)
         return __cosf(a);
 #else
@@ -87,7 +104,7 @@ template <bool EXACT> struct M
     // powf(x, 5) (Maths.h:331)
     static TPT_HD float pow5_(float x)
     {
-        if (EXACT) return tptlibm::powf_glibc(x, 5.0f);
+        if (EXACT) return exact_pow5f(x);
         float x2 = x * x;
         return x2 * x2 * x;
     }
@@ -775,6 +792,9 @@ TPT_D void xpath_sample(const SceneView& sc, const Camera88& cam, int x, int y, 
             V3 target = pos + normal + RandomUnitVector<true>(rng);       // Test.cpp:89-92
             V3 outDir = M<true>::normalize(target - pos);
             const uint32_t rngLights = rng;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
             for (int j = 0; j < sc.nLights; ++j)                          // Test.cpp:96-122: 2 draws + 1 ray per light
                 if (sc.lights[j].id != mid) { XorShift32(rng); XorShift32(rng); ++rayCount; }
             emit(XE_LAMBERT, mid, pos, normal, r.dir, rngLights);
@@ -826,6 +846,9 @@ TPT_D bool xshade_event(const SceneView& sc, XShade& sh, int type, int mid, V3 a
             return false;
         }
     }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
     for (int k = sh.n - 1; k >= 0; --k) result = sh.e[k] + sh.a[k] * result;   // Test.cpp:216, back to front
     return true;
 }

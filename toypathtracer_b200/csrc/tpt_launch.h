@@ -11,6 +11,7 @@ struct SceneDev
     SceneBlobLayout layout;
     int count, nLights;
     uint32_t stagedBytes;        // prefix of the blob every CTA stages into shared memory via TMA
+    int kformMode;               // fast kernels: 2 = expanded form with packed pairs (FFMA2) where it fits, 1 = expanded form, scalar
     bool kformOk;                // every sphere satisfies |c|^2 <= 128 + 2 r^2: the expanded-form sweep of the fast kernels
                                  // then rounds no worse than the reference form (see FastHitterK)
 };
@@ -29,5 +30,6 @@ cudaError_t launch_refgpu_exact(const DrawParams& p, const SceneDev& sc, int num
 cudaError_t launch_refgpu_fast(const DrawParams& p, const SceneDev& sc, int numSMs, cudaStream_t stream);
 int fast_slab_pixels();
 int fast_kernel_launches(const DrawParams& p, int variant);
+bool fast_variant_writes_final_pixels(int variant);   // the trace kernel stores finished pixels itself (no L2 reductions)
 
 } // namespace tpt
