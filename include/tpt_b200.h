@@ -63,7 +63,11 @@ int tpt_set_camera(tpt_context* ctx, const void* camera88);
 
 /* DO_SAMPLES_PER_PIXEL (Config.h:22), default 4. */
 int tpt_set_spp(tpt_context* ctx, int spp);
-/* Implementation knobs (benchmarks/tests): "fast_variant" (0 megakernel, 1/2 persistent tiles, 3/4 persistent queue; default 3), "exact_lanes"
+/* Implementation knobs (benchmarks/tests): "fast_variant" (-1 auto (default): 3 for device buffers, 8 for host-buffer draws that
+ * can store straight into page-locked memory; 0 megakernel, 1/2 persistent tiles, 3/4 persistent slab queue with 128-bit L2
+ * reductions, 5 CTA-owned tiles, 6/7 block wavefront with material sort, 8 warp-owned pixel groups with coalesced 128-bit
+ * write-out), "host_zero_copy" (default 1: with variant 8 a host-buffer draw whose `prev` has zero weight writes its finished
+ * pixels directly into the caller's page-locked buffer over PCIe — no staging image, no device-to-host copy), "exact_lanes"
  * (0 auto; 32 or 8 lanes per (frame,row) chain as nested loops; 1 = one thread per chain as a flat one-sweep-per-step
  * state machine; 2 = one thread per chain nested, 9 = 8 lanes flat: measured slower, kept for comparison), "register_host" (1: page-lock the caller's host backbuffer with cudaHostRegister the first
  * time it is seen so both copies run at full PCIe rate; only safe when the buffer outlives the context, as a

@@ -137,8 +137,9 @@ def test_expanded_form_sweep_matches_reference_form(gpu_ctx):
         rays = gpu_ctx.draw(0, 16, W, H, img, flags=2, mode=1)
         out.append((img, rays))
     gpu_ctx.set_option("fast_kform", 2)
-    # packed pairs (FFMA2) evaluate exactly the scalar expanded form's products: same candidates, same paths
-    assert out[0][1] == out[1][1] and rel_l2(out[0][0], out[1][0]) < 1e-5
+    # packed pairs (FFMA2) evaluate the scalar expanded form's products: the same paths except for a handful of decisions
+    # per 10^7 rays (measured: 10 rays of 67 M differ)
+    assert abs(out[0][1] / out[1][1] - 1) < 1e-6 and rel_l2(out[0][0], out[1][0]) < 1e-3
     assert abs(out[1][1] / out[2][1] - 1) < 1e-4
     assert rel_l2(out[1][0], out[2][0]) < 3e-3
 
@@ -203,9 +204,20 @@ def test_zero_copy_host_write_out(gpu_ctx):
         # progressive (prev has weight): staged path, alpha preserved
         pinned[...] = 0.0; pinned[..., 3] = 0.5
         seq = np.zeros((H, W, 4), np.float32); seq[..., 3] = 0.5
-        for f in range(3):
+        for f in range(1, 4):                                   # frame 0 has lerpFac 0: prev would have no weight
             gpu_ctx.draw(f, 1, W, H, pinned, flags=2, mode=1)
             gpu_ctx.draw(f, 1, W, H, seq, flags=2, mode=1)
         assert rel_l2(pinned, seq) < 1e-5 and (pinned[..., 3] == 0.5).all()
+        # default options ("fast_variant" -1 = auto): a pinned host buffer takes the zero-copy kernel (1 trace launch + the
+        # ray-count fold), a device buffer the slab queue (prepare + trace + fold)
+        import toypathtracer_b200 as tpt
+        ctx2 = tpt.Context(0)
+        ctx2.set_scene(sph, mats, cam, em)
+        pinned[...] = 3.0
+        assert ctx2.draw(7, 1, W, H, pinned, flags=0, mode=1) == rays_ref and ctx2.last_launch_count() == 2
+        assert rel_l2(pinned, ref) < 1e-5
+        dev = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+        assert ctx2.draw(7, 1, W, H, dev, flags=0, mode=1) == rays_ref and ctx2.last_launch_count() == 3
+        ctx2.close()
     finally:
         gpu_ctx.set_option("fast_variant", 3)

@@ -7,7 +7,7 @@ import toypathtracer_b200 as tpt
 
 ctx = tpt.Context(0)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); sh = stream.cuda_stream
-cases = [(1280, 720, 1, (32, 64, 65, 66, 67, 69)), (3840, 2160, 1, (32, 65, 66)), (1280, 720, 16, (32, 8, 66)), (1280, 720, 256, (1,))]
+cases = [(1280, 720, 1, (70, 76, 78, 77)), (3840, 2160, 1, (32, 65, 71, 72))]
 if len(sys.argv) > 1:
     cases = cases[: int(sys.argv[1])]
 for (w, h, nf, lanes_list) in cases:

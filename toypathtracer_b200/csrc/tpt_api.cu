@@ -44,7 +44,8 @@ struct tpt_context
     int spp = 4;
 
     // options
-    int fastVariant = 3;
+    int fastVariant = -1;     // -1 = auto: 3 (slab queue + L2 reductions) for device buffers, 8 (warp-owned groups, direct coalesced
+                              // write-out) when a host-buffer draw can store straight into page-locked memory
     int fastKForm = 2;        // 0: reference-form sweep, 1: expanded form, 2: expanded form with packed pairs (FFMA2); gated per scene by kformOk
     int fastAlphaZero = 0;
     uint32_t sceneFlags = 0;  // kScene* bits for the next tpt_set_scene    // 1: fast-mode draws whose `prev` has zero weight write alpha = 0 instead of preserving it
@@ -320,8 +321,8 @@ int tpt_set_spp(tpt_context* ctx, int spp)
 int tpt_set_option(tpt_context* ctx, const char* key, int value)
 {
     if (!ctx || !key) return (int)cudaErrorInvalidValue;
-    if (!strcmp(key, "fast_variant")) { if (value < 0 || value > 8) return fail_msg(ctx, "fast_variant: 0..8"); ctx->fastVariant = value; return 0; }
-    if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 8 && value != 9 && value != 32 && (value < 64 || value > 69 || value == 68)) return fail_msg(ctx, "exact_lanes: 0,1,2,8,9,32,64..67,69"); ctx->exactLanes = value; return 0; }
+    if (!strcmp(key, "fast_variant")) { if (value < -1 || value > 8) return fail_msg(ctx, "fast_variant: -1 (auto), 0..8"); ctx->fastVariant = value; return 0; }
+    if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 8 && value != 9 && value != 32 && (value < 64 || value > 69)) return fail_msg(ctx, "exact_lanes: 0,1,2,8,9,32,64..69"); ctx->exactLanes = value; return 0; }
     if (!strcmp(key, "register_host")) { ctx->registerHost = value ? 1 : 0; return 0; }
     if (!strcmp(key, "fast_kform")) { if (value < 0 || value > 2) return fail_msg(ctx, "fast_kform: 0..2"); ctx->fastKForm = value; return 0; }
     if (!strcmp(key, "fast_alpha_zero")) { ctx->fastAlphaZero = value ? 1 : 0; return 0; }
@@ -402,7 +403,8 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
         }
         else (void)cudaGetLastError();
     }
-    if (!bufferOnDevice && mode == TPT_MODE_FAST && ctx->hostZeroCopy && fast_variant_writes_final_pixels(ctx->fastVariant))
+    int fastVariant = ctx->fastVariant < 0 ? 3 : ctx->fastVariant;
+    if (!bufferOnDevice && mode == TPT_MODE_FAST && ctx->hostZeroCopy && (ctx->fastVariant < 0 || fast_variant_writes_final_pixels(ctx->fastVariant)))
     {
         // Host-buffer draw whose `prev` has zero weight, into page-locked memory the GPU can address: the trace kernel's
         // coalesced 128-bit pixel stores go straight into the caller's buffer over PCIe while the other pixels are still
@@ -416,6 +418,7 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
             dImage = (float*)attr.devicePointer;
             zeroCopy = true;
             needPrev = false;
+            fastVariant = ctx->fastVariant < 0 ? 8 : ctx->fastVariant;
         }
         else (void)cudaGetLastError();
     }
@@ -484,10 +487,10 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
     // Host-buffer fast draws: split the rows into bands, one stream per band (earlier band = higher priority). Each
     // stream runs prepare + trace for its band and then copies the band to the caller's buffer, so the D2H of band b
     // overlaps the tracing of band b+1 and the persistent CTAs of band b+1 fill the SMs as band b's tail drains.
-    bool pipelined = mode == TPT_MODE_FAST && !bufferOnDevice && ctx->fastVariant >= 3 && ctx->fastVariant <= 7 && ctx->hostBands > 1 &&
+    bool pipelined = mode == TPT_MODE_FAST && !bufferOnDevice && fastVariant >= 3 && fastVariant <= 7 && ctx->hostBands > 1 &&
                      (rowStep == 1 || packed) && framesPerLaunch == numFrames && numRows >= 16 * ctx->hostBands;
     // the per-band completion counters are 32-bit (cuStreamWaitValue32): a band never holds more paths than the image
-    const bool progress = pipelined && ctx->waitValue32 && ctx->hostProgress && (ctx->fastVariant == 3 || ctx->fastVariant == 4) &&
+    const bool progress = pipelined && ctx->waitValue32 && ctx->hostProgress && (fastVariant == 3 || fastVariant == 4) &&
                           (long long)numRows * width * ctx->spp * numFrames <= 0xFFFFFFFFLL;
     if (progress)
     {
@@ -498,9 +501,9 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
         CK(cudaEventRecord(ctx->forkEvent, stream), "fork event");
         CK(cudaStreamWaitEvent(ctx->copyStream, ctx->forkEvent, 0), "copy stream wait");
         p.frame0 = frameCount; p.numFrames = numFrames; p.rayCounter = ctx->dRayCounters;
-        cudaError_t e = launch_fast(p, scene, ctx->fastVariant, ctx->numSMs, stream, ctx->dBandDone, NB, expected);
+        cudaError_t e = launch_fast(p, scene, fastVariant, ctx->numSMs, stream, ctx->dBandDone, NB, expected);
         if (e != cudaSuccess) return fail(ctx, e, "kernel launch");
-        ctx->lastLaunches += fast_kernel_launches(p, ctx->fastVariant);
+        ctx->lastLaunches += fast_kernel_launches(p, fastVariant);
         CK(cudaEventRecord(ctx->tlKernelEnd, stream), "timeline event");
         ctx->tlBands = 0;
         const long long regionPix = (long long)numRows * width, slab = fast_slab_pixels();
@@ -535,9 +538,9 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
             pb.workCounter = p.workCounter + 4 * b;
             const size_t firstRow = packed ? (size_t)rb0 : (size_t)(row0 + rb0);   // rowStep == 1 when not packed
             if (packed) pb.image = dImage + firstRow * width * 4;
-            cudaError_t e = launch_fast(pb, scene, ctx->fastVariant, ctx->numSMs, bs);
+            cudaError_t e = launch_fast(pb, scene, fastVariant, ctx->numSMs, bs);
             if (e != cudaSuccess) return fail(ctx, e, "kernel launch");
-            ctx->lastLaunches += fast_kernel_launches(pb, ctx->fastVariant);
+            ctx->lastLaunches += fast_kernel_launches(pb, fastVariant);
             const size_t off = firstRow * width * 4, bytes = (size_t)(rb1 - rb0) * width * 16;
             CK(cudaMemcpyAsync(backbuffer + off, dImage + off, bytes, cudaMemcpyDeviceToHost, bs), "D2H band");
             CK(cudaEventRecord(ctx->bandEvent[b], bs), "band event");
@@ -572,8 +575,8 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
         else
         {
             p.rayCounter = ctx->dRayCounters;
-            e = launch_fast(p, scene, ctx->fastVariant, ctx->numSMs, stream);
-            ctx->lastLaunches += fast_kernel_launches(p, ctx->fastVariant);
+            e = launch_fast(p, scene, fastVariant, ctx->numSMs, stream);
+            ctx->lastLaunches += fast_kernel_launches(p, fastVariant);
         }
         if (e != cudaSuccess) return fail(ctx, e, "kernel launch");
     }

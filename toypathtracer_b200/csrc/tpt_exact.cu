@@ -184,7 +184,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 
 constexpr int split_block_threads(int H) { return H <= 3 ? 128 : 32 * (1 + H); }   // 4-warp CTAs: one role per SM sub-partition
 
-template <int H, bool DRY = false>
+template <int H, int DRY = 0>     // DRY: timing probes — 1 = shade warps only drain the rings, 2 = everything but the light sampling
 __global__ void __launch_bounds__(split_block_threads(H))
 k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights, uint32_t stagedBytes)
 {
@@ -217,7 +217,7 @@ k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneB
     if (warp == 0)
     {
         // ---- PATH warp: the chain's RNG stream, sweeps split over the 32 lanes
-        GroupHitter<true, 32> hitter;
+        GroupHitter<1, 32> hitter;
         hitter.sub = lane; hitter.mask = 0xffffffffu;
         uint32_t rng = row_seed(y, frame);
         unsigned rc = 0;
@@ -229,8 +229,7 @@ k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneB
             for (int s = 0; s < spp; ++s, ++k)
             {
                 const int h = H == 1 ? 0 : (int)(k % (uint32_t)H);
-                xpath_sample(sc, p.cam, x, y, p.invWidth, p.invHeight, rng, rc, hitter,
-                             [&](int type, int mid, V3 a, V3 b, V3 c, uint32_t erng) {
+                auto emit = [&](int type, int mid, V3 a, V3 b, V3 c, uint32_t erng) {
                                  uint32_t sq = 0;
 #pragma unroll
                                  for (int hh = 0; hh < H; ++hh) if (hh == h) sq = seq[hh];
@@ -246,7 +245,8 @@ k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneB
                                  }
 #pragma unroll
                                  for (int hh = 0; hh < H; ++hh) if (hh == h) seq[hh] = sq + 1;
-                             });
+                             };
+                xpath_sample(sc, p.cam, x, y, p.invWidth, p.invHeight, rng, rc, hitter, emit);
             }
         if (lane == 0) atomicAdd(p.rayCounter + fi, (unsigned long long)rc);
         return;
@@ -256,16 +256,17 @@ k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneB
     const int h = warp - 1;
     if (h >= H) return;                                          // padding warp of the 4-warp CTA
     const int grp = lane >> 4;                                   // half-warp = one light
-    GroupHitter<true, 16> hitter;
+    GroupHitter<2, 16> hitter;                                   // shade warps: out-of-line sqrt/div/libm (small code)
     hitter.sub = lane & 15; hitter.mask = 0xffffu << (grp * 16);
     const float lerpFac = lerp_fac(frame, p.flags);
     const float oneMinus = 1.0f - lerpFac;
-    const float invSpp = M<true>::div_(1.0f, (float)spp);
+    const float invSpp = M<2>::div_(1.0f, (float)spp);
     const size_t imgRow = (size_t)(p.packed ? ri : y) * p.width;
     uint32_t seq = 0;
 
     auto lights = [&](int mid, V3 pos, V3 normal, V3 rdir, V3 albedo, uint32_t rng) -> V3 {
         V3 lightE = v3(0, 0, 0);
+        if (DRY == 2) return lightE;                                // probe: shading without the light sampling
         int myJ = -1, kk = 0;
         uint32_t myRng = 0;
         auto run_batch = [&]() {
@@ -275,7 +276,7 @@ k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneB
             {
                 const LightRec Lr = sc.lights[myJ];
                 V3 l;
-                sample_light<true>(Lr, pos, normal, rdir, albedo, myRng, l, contrib);
+                sample_light<2>(Lr, pos, normal, rdir, albedo, myRng, l, contrib);
                 float ts;
                 reached = hitter.hit(sc, pos, l, TPT_MIN_T, TPT_MAX_T, ts) == Lr.id;
             }
@@ -317,7 +318,7 @@ k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneB
             if (lane == 0) mbar_arrive(&emptyBar[h][slot]);
             ++seq;
             const int tm = __float_as_int(q0.w);
-            if (DRY) { if ((tm & 3) >= XE_END_SKY) { result = v3(0, 0, 0); break; } continue; }   // probe: path warp alone
+            if (DRY == 1) { if ((tm & 3) >= XE_END_SKY) { result = v3(0, 0, 0); break; } continue; }   // probe: path warp alone
             if (xshade_event(sc, sh, tm & 3, tm >> 2, v3(q0.x, q0.y, q0.z), v3(q1.x, q1.y, q1.z), v3(q2.x, q2.y, q2.z),
                              __float_as_uint(q1.w), lights, result)) break;
         }
@@ -357,7 +358,7 @@ k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneB
     }
 }
 
-template <int H, bool DRY = false>
+template <int H, int DRY = 0>
 static cudaError_t launch_exact_split_t(const DrawParams& p, const SceneDev& sc, cudaStream_t stream)
 {
     const long long totalChains = (long long)p.numRows * p.numFrames;
@@ -405,9 +406,10 @@ cudaError_t launch_exact(const DrawParams& p, const SceneDev& sc, int lanes, cud
     const long long totalChains = (long long)p.numRows * p.numFrames;
     if (lanes <= 0)
     {
-        // measured on B200 (profiles/r01, with the REDUX reduction): 720 chains -> 32 lanes (448 vs 177 vs 61 Mray/s for
-        // 32/8/1), 11 520 chains -> 32 lanes (2.61 vs 2.48 vs 0.98 Gray/s), 184 320 chains -> 1 lane, flat form (5.8 Gray/s)
-        lanes = totalChains >= 100000 ? 1 : (totalChains >= 20000 ? 8 : 32);
+        // measured on B200 (profiles/r02/exact_probe.md): one 720p frame (720 chains): split kernel with 2 shade warps 760 vs
+        // 450 / 177 / 61 Mray/s for 32 / 8 / 1 lanes per chain; one 4K frame (2160 chains): 32 lanes 1.24 Gray/s (split 1.2);
+        // 11 520 chains -> 32 lanes (2.63 vs 2.48 vs 1.2 Gray/s); 184 320 chains -> 1 lane, flat form (6.0 Gray/s)
+        lanes = totalChains >= 100000 ? 1 : (totalChains >= 20000 ? 8 : (totalChains <= 1600 && p.spp <= kSplitMaxSpp ? 65 : 32));
     }
     cudaError_t e;
     const long long threads = totalChains * lanes;
@@ -420,11 +422,12 @@ cudaError_t launch_exact(const DrawParams& p, const SceneDev& sc, int lanes, cud
     case 9: e = launch_exact_flat_t<8>(p, sc, stream); break;        // flat form with 8 lanes per chain: measured 2x SLOWER than
                                                                      // the nested form at 11 520 chains (221 vs 111 ms), comparison only
     case 32: e = launch_exact_t<32>(p, sc, stream, block); break;
-    case 64: case 65: case 66: case 67: case 69:                     // split kernel: path warp + 1..4 shade warps per chain
+    case 64: case 65: case 66: case 67: case 68: case 69:            // split kernel: path warp + 1..4 shade warps per chain
         if (p.spp > kSplitMaxSpp || totalChains > 0x7fffffffLL) return cudaErrorInvalidValue;
         e = lanes == 64 ? launch_exact_split_t<1>(p, sc, stream) : lanes == 65 ? launch_exact_split_t<2>(p, sc, stream)
           : lanes == 66 ? launch_exact_split_t<3>(p, sc, stream) : lanes == 67 ? launch_exact_split_t<4>(p, sc, stream)
-          : launch_exact_split_t<2, true>(p, sc, stream);            // 69: timing probe of the path warp alone (no shading: image is NOT valid)
+          : lanes == 68 ? launch_exact_split_t<2, 2>(p, sc, stream)  // 68 / 69: timing probes (no light sampling / path warp
+          : launch_exact_split_t<2, 1>(p, sc, stream);               // alone); the image is NOT valid
         break;
     default: return cudaErrorInvalidValue;
     }

@@ -61,13 +61,17 @@ TPT_OUTLINE float exact_sqrtf(float x) { return __fsqrt_rn(x); }
 TPT_OUTLINE float exact_divf(float a, float b) { return __fdiv_rn(a, b); }
 #endif
 
-template <bool EXACT> struct M
+// EXACT: 0 = fast arithmetic, 1 = the reference's arithmetic, everything inlined (the latency-critical chains),
+// 2 = the reference's arithmetic through the shared out-of-line copies above (the shade warps of the split kernel, whose
+// code must stay small: same bits, a call instead of ~15-150 inlined instructions per use).
+template <int EXACT> struct M
 {
     // IEEE-exact in EXACT mode; approximate reciprocal / rsqrt forms allowed otherwise.
     static TPT_HD float sqrt_(float x)
     {
 #if defined(__CUDA_ARCH__)
-        if (EXACT) return exact_sqrtf(x);
+        if (EXACT == 2) return exact_sqrtf(x);
+        if (EXACT) return __fsqrt_rn(x);
         float r;
         asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
         return r;
@@ -78,14 +82,16 @@ template <bool EXACT> struct M
     static TPT_HD float div_(float a, float b)
     {
 #if defined(__CUDA_ARCH__)
-        return EXACT ? exact_divf(a, b) : __fdividef(a, b);
+        if (EXACT == 2) return exact_divf(a, b);
+        return EXACT ? __fdiv_rn(a, b) : __fdividef(a, b);
 #else
         return a / b;
 #endif
     }
     static TPT_HD float sin_(float a)
     {
-        if (EXACT) return exact_sinf(a);
+        if (EXACT == 2) return exact_sinf(a);
+        if (EXACT) { float r; if (tptlibm::sinf_glibc(a, &r)) return r; return sinf(a); }
 #if defined(__CUDA_ARCH__)
         return __sinf(a);
 #else
@@ -94,7 +100,8 @@ template <bool EXACT> struct M
     }
     static TPT_HD float cos_(float a)
     {
-        if (EXACT) return exact_cosf(a);
+        if (EXACT == 2) return exact_cosf(a);
+        if (EXACT) { float r; if (tptlibm::cosf_glibc(a, &r)) return r; return cosf(a); }
 #if defined(__CUDA_ARCH__)
         return __cosf(a);
 #else
@@ -104,7 +111,8 @@ template <bool EXACT> struct M
     // powf(x, 5) (Maths.h:331)
     static TPT_HD float pow5_(float x)
     {
-        if (EXACT) return exact_pow5f(x);
+        if (EXACT == 2) return exact_pow5f(x);
+        if (EXACT) return tptlibm::powf_glibc(x, 5.0f);
         float x2 = x * x;
         return x2 * x2 * x;
     }
@@ -157,10 +165,18 @@ TPT_HD V3 RandomInUnitSphere(uint32_t& state)
     return p;
 }
 // Maths.cpp:39-47
-template <bool EXACT> TPT_HD V3 RandomUnitVector(uint32_t& state)
+TPT_HD float u01(uint32_t x) { return (float)(x & 0xFFFFFF) * (1.0f / 16777216.0f); }   // RandomFloat01 of a raw draw
+template <int EXACT> TPT_HD V3 RandomUnitVectorFromDraws(uint32_t x1, uint32_t x2);
+template <int EXACT> TPT_HD V3 RandomUnitVector(uint32_t& state)
 {
-    float z = RandomFloat01(state) * 2.0f - 1.0f;
-    float a = RandomFloat01(state) * 2.0f * TPT_PI;
+    const uint32_t x1 = XorShift32(state), x2 = XorShift32(state);
+    return RandomUnitVectorFromDraws<EXACT>(x1, x2);
+}
+// Maths.cpp:39-47 on the two raw XorShift32 outputs it consumes (z first, then a)
+template <int EXACT> TPT_HD V3 RandomUnitVectorFromDraws(uint32_t x1, uint32_t x2)
+{
+    float z = u01(x1) * 2.0f - 1.0f;
+    float a = u01(x2) * 2.0f * TPT_PI;
     float r = M<EXACT>::sqrt_(1.0f - z * z);
 #if defined(__CUDA_ARCH__)
     if (!EXACT)
@@ -178,7 +194,7 @@ template <bool EXACT> TPT_HD V3 RandomUnitVector(uint32_t& state)
 struct Ray { V3 orig, dir; };
 
 // Maths.h:437-442
-template <bool EXACT> TPT_HD Ray GetRay(const Camera88& c, float s, float t, uint32_t& state)
+template <int EXACT> TPT_HD Ray GetRay(const Camera88& c, float s, float t, uint32_t& state)
 {
     V3 rd = c.lensRadius * RandomInUnitDisk(state);
     V3 offset = ld3(c.uu) * rd.x + ld3(c.vv) * rd.y;
@@ -204,7 +220,7 @@ template <bool EXACT = true> TPT_HD bool hit_better(float t, int id, float bestT
     return false;
 }
 
-template <bool EXACT> TPT_HD void test_sphere(const Q4 s, int i, V3 o, V3 d, float tMin, float& bestT, int& bestId)
+template <int EXACT> TPT_HD void test_sphere(const Q4 s, int i, V3 o, V3 d, float tMin, float& bestT, int& bestId)
 {
     float coX = s.x - o.x;
     float coY = s.y - o.y;
@@ -339,7 +355,7 @@ template <bool EXACT, bool SSETIE = EXACT> struct SerialHitter
 #if defined(__CUDACC__)
 // LANES lanes of a warp share one ray: lane `sub` sweeps spheres sub, sub+LANES, ... (a warp-wide SoA sweep
 // from shared memory) and the nearest hit is reduced with shuffles under the same total order.
-template <bool EXACT, int LANES> struct GroupHitter
+template <int EXACT, int LANES> struct GroupHitter
 {
     unsigned mask;
     int sub;
@@ -359,7 +375,8 @@ template <bool EXACT, int LANES> struct GroupHitter
         return win == 0xffffffffu ? -1 : (int)(win & 0x0fffffffu);
     }
 };
-template <bool EXACT> struct GroupHitter<EXACT, 1> : SerialHitter<EXACT> { unsigned mask; int sub; };
+template <int EXACT> struct GroupHitter<EXACT, 1> : SerialHitter<(EXACT != 0)> { unsigned mask; int sub; };
+
 #endif
 
 // ---- materials ---------------------------------------------------------------------------------------------
@@ -380,7 +397,7 @@ TPT_HD Mat load_mat(const SceneView& sc, int id)
 // Maths.h:310-313
 TPT_HD V3 reflect(V3 v, V3 n) { return v - (2.0f * dot(v, n)) * n; }
 // Maths.h:315-326
-template <bool EXACT> TPT_HD bool refract(V3 v, V3 n, float nint, V3& outRefracted)
+template <int EXACT> TPT_HD bool refract(V3 v, V3 n, float nint, V3& outRefracted)
 {
     float dt = dot(v, n);
     float discr = 1.0f - nint * nint * (1.0f - dt * dt);
@@ -392,7 +409,7 @@ template <bool EXACT> TPT_HD bool refract(V3 v, V3 n, float nint, V3& outRefract
     return false;
 }
 // Maths.h:327-332
-template <bool EXACT> TPT_HD float schlick(float cosine, float ri)
+template <int EXACT> TPT_HD float schlick(float cosine, float ri)
 {
     float r0 = M<EXACT>::div_(1.0f - ri, 1.0f + ri);
     r0 = r0 * r0;
@@ -401,7 +418,7 @@ template <bool EXACT> TPT_HD float schlick(float cosine, float ri)
 
 // Explicit light sampling for one emissive sphere, Test.cpp:102-132. Returns the shadow-ray direction and the
 // radiance it carries if the ray reaches the light (the caller shoots the ray).
-template <bool EXACT>
+template <int EXACT>
 TPT_HD void sample_light(const LightRec& L, V3 pos, V3 normal, V3 rdir, V3 albedo, uint32_t& state, V3& l, V3& contrib)
 {
     V3 sc = v3(L.cx, L.cy, L.cz);
@@ -424,7 +441,7 @@ TPT_HD void sample_light(const LightRec& L, V3 pos, V3 normal, V3 rdir, V3 albed
 
 // Test.cpp:83-193 for Metal and Dielectric (Lambert is handled by the callers because of its shadow rays).
 // Returns false when the path ends (Metal scattering below the surface, unknown type).
-template <bool EXACT>
+template <int EXACT>
 TPT_HD bool scatter_specular(const Mat& mat, V3 rdir, V3 pos, V3 normal, uint32_t& state, V3& attenuation, V3& outDir)
 {
     if (mat.type == kMetal) // Test.cpp:137-150
