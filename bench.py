@@ -413,7 +413,43 @@ def main():
             ex_rays = ctx.read_ray_count(sh)
             ex_ms = ev0.elapsed_time(ev1)
             line["exact_mode"] = {"value": ex_rays / ex_ms / 1e3, "unit": "Mray/s", "ms_per_step": ex_ms / ex_steps, "steps": ex_steps,
-                                  "note": "TPT_MODE_EXACT: pixels and ray counts bit-identical to the reference CPU path"}
+                                  "note": "TPT_MODE_EXACT: pixels and ray counts bit-identical to the reference CPU path; one frame "
+                                          "traced per call (720 serial RNG chains: latency-bound)"}
+            # the same calls with frame lookahead: a cache miss traces 16 consecutive frames in one launch, the next 15
+            # one-frame calls only blend their cached frame (same bits, same counts; amortised over 32 calls = 2 misses)
+            ctx.set_option("exact_lookahead", 16)
+            for s_ in range(16):
+                ctx.draw(100 + s_, 1, W, H, image, flags=0, mode=tpt.MODE_EXACT, stream=sh, want_rays=False)
+            ctx.read_ray_count(sh)
+            ev0.record(stream)
+            for s_ in range(32):
+                ctx.draw(116 + s_, 1, W, H, image, flags=0, mode=tpt.MODE_EXACT, stream=sh, want_rays=False)
+            ev1.record(stream)
+            torch.cuda.synchronize(dev)
+            la_rays = ctx.read_ray_count(sh)
+            la_ms = ev0.elapsed_time(ev1)
+            ctx.set_option("exact_lookahead", 0)
+            line["exact_mode_lookahead16"] = {"value": la_rays / la_ms / 1e3, "unit": "Mray/s", "ms_per_step": la_ms / 32, "steps": 32,
+                                              "note": "exact_lookahead = 16: amortised over 32 one-frame calls (2 trace launches of 16 "
+                                                      "frames + 32 blends); first-call latency = 16 frames"}
+        if world == 1 and args.mode == "fast":
+            # the reference-GPU-compatible estimator (per-pixel seeds, ComputeShader.hlsl) on the same frame: like for like
+            # with the numbers the reference publishes for its own GPU back-ends (readme.md:64-77, other hardware)
+            rg = {}
+            for name, m in (("strict", tpt.MODE_REFGPU), ("native", tpt.MODE_REFGPU_FAST)):
+                for s_ in range(2):
+                    ctx.draw(s_, 1, W, H, image, flags=0, mode=m, stream=sh, want_rays=False)
+                ctx.read_ray_count(sh)
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record(stream)
+                for s_ in range(10):
+                    ctx.draw(2 + s_, 1, W, H, image, flags=0, mode=m, stream=sh, want_rays=False)
+                ev1.record(stream)
+                torch.cuda.synchronize(dev)
+                rg[name] = {"value": ctx.read_ray_count(sh) / ev0.elapsed_time(ev1) / 1e3, "unit": "Mray/s", "ms_per_step": ev0.elapsed_time(ev1) / 10}
+            rg["note"] = ("TPT_MODE_REFGPU / _FAST: the estimator of Cpp/Windows/ComputeShader.hlsl; the reference's readme.md reports "
+                          "3920 Mray/s (D3D11, GeForce RTX 3080 Ti) and 1680 Mray/s (Metal, M4 Max) for its own GPU paths on this workload")
+            line["refgpu_mode"] = rg
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline_sample()

@@ -68,8 +68,10 @@ int tpt_set_spp(tpt_context* ctx, int spp);
  * reductions, 5 CTA-owned tiles, 6/7 block wavefront with material sort, 8 warp-owned pixel groups with coalesced 128-bit
  * write-out), "host_zero_copy" (default 1: with variant 8 a host-buffer draw whose `prev` has zero weight writes its finished
  * pixels directly into the caller's page-locked buffer over PCIe — no staging image, no device-to-host copy), "exact_lanes"
- * (0 auto; 32 or 8 lanes per (frame,row) chain as nested loops; 1 = one thread per chain as a flat one-sweep-per-step
- * state machine; 2 = one thread per chain nested, 9 = 8 lanes flat: measured slower, kept for comparison), "register_host" (1: page-lock the caller's host backbuffer with cudaHostRegister the first
+ * (0 auto; 64..67 = split kernel: one PATH warp per (frame,row) chain walks the RNG stream, 1..4 SHADE warps do the light
+ * sampling / fold / blend off the critical path (auto for <= 1600 chains); 32 or 8 lanes per chain as nested loops; 1 = one
+ * thread per chain as a flat one-sweep-per-step state machine (auto for >= 100 000 chains); 2 = one thread per chain
+ * nested, 9 = 8 lanes flat: measured slower, kept for comparison; 68/69 timing probes), "register_host" (1: page-lock the caller's host backbuffer with cudaHostRegister the first
  * time it is seen so both copies run at full PCIe rate; only safe when the buffer outlives the context, as a
  * reference shell's does; default 0 — buffers that are already pinned are detected by CUDA on their own), "host_bands" (1..8, default 3:
  * host-buffer fast draws are split into row bands on separate streams so the D2H of one band overlaps the tracing of
@@ -79,6 +81,11 @@ int tpt_set_spp(tpt_context* ctx, int spp);
  * spheres per instruction with Blackwell's packed fma.rn.f32x2; 1 and 2 only when the scene passes the gate in
  * tpt_set_scene; per context), "fast_alpha_zero" (default 0; 1: fast-mode draws whose `prev` has zero weight write
  * alpha = 0 instead of keeping the buffer's alpha — saves the read over NVLink when the buffer is a peer GPU's),
+ * "exact_lookahead" (default 0; L > 1: an exact-mode draw of ONE frame that misses the cache traces frames [f, f+L) in a
+ * single launch and keeps their per-frame colours; the calls for the following frames only blend their cached frame into
+ * the caller's buffer. Bit-identical results and per-frame ray counts; trades L frames of latency on a miss for batch
+ * throughput (one 720p frame alone cannot fill the GPU: `height` serial RNG chains). Never used with kFlagAnimate; any
+ * scene / camera / size / row-range / spp change invalidates the cache),
  * "mitsuba_compare" (default 0; DO_MITSUBA_COMPARE of Config.h:25 as a runtime switch, applied by the NEXT
  * tpt_set_scene: constant sky (0.15, 0.21, 0.3) (Test.cpp:226-227) and zero Metal roughness (Test.cpp:143-145); the
  * switch's third effect, zero aperture (Test.cpp:312-313), is camera data: the Test.h shim's UpdateTest applies it). */

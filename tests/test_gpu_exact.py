@@ -253,3 +253,41 @@ def test_frame_batches_limited_by_scratch(gpu_ctx, oracle):
     t2, pf2 = gpu_ctx.draw(0, 3, big_w, big_h, b2, flags=2, mode=0, per_frame=True)
     gpu_ctx.set_option("max_scratch_mb", 8192)
     assert pf2 == r2 and not bits_differ(b2, o2, p2).any()
+
+
+def test_frame_lookahead_is_bit_identical(libs, oracle):
+    """"exact_lookahead": a miss traces L frames in one launch, the following one-frame calls only blend their cached
+    frame — same pixels, same per-frame ray counts as frame-by-frame draws; scene/camera/size changes invalidate."""
+    ctx = libs.Context(0)
+    sph, mats, cam, em = golden_scene()
+    w, h = 192, 108
+    ctx.set_scene(sph, mats, cam, em)
+    ref = np.zeros((h, w, 4), np.float32)
+    ref_rays = [ctx.draw(f, 1, w, h, ref, flags=2, mode=0) for f in range(13)]
+    ctx.set_option("exact_lookahead", 5)
+    buf = np.zeros((h, w, 4), np.float32)
+    rays = []
+    launches = []
+    for f in range(13):
+        ctx.set_scene(sph, mats, cam, em)                         # a shell calls UpdateTest every frame: same bytes, cache stays
+        rays.append(ctx.draw(f, 1, w, h, buf, flags=2, mode=0))
+        launches.append(ctx.last_launch_count())
+    assert rays == ref_rays and not bits_differ(buf, ref).any()
+    assert launches[0] == 3 and launches[1] == 2 and launches[5] == 3     # miss: trace + resolve + fold; hit: resolve + fold
+    # a different scene mid-way: the cached frames of the old scene must not be used
+    m2 = mats.copy(); m2.view(np.float32).reshape(-1, 9)[0, 1:4] = (0.2, 0.9, 0.2)
+    a = np.zeros((h, w, 4), np.float32); b = np.zeros((h, w, 4), np.float32)
+    ctx.set_option("exact_lookahead", 0)
+    ctx.set_scene(sph, mats, cam, em); ctx.draw(20, 1, w, h, a, flags=0, mode=0)
+    ctx.set_scene(sph, m2, cam, em); ra = ctx.draw(21, 1, w, h, a, flags=0, mode=0)
+    ctx.set_option("exact_lookahead", 4)
+    ctx.set_scene(sph, mats, cam, em); ctx.draw(20, 1, w, h, b, flags=0, mode=0)
+    ctx.set_scene(sph, m2, cam, em); rb = ctx.draw(21, 1, w, h, b, flags=0, mode=0)
+    assert ra == rb and not bits_differ(a, b).any()
+    # non-progressive flags, a row shard, and an animated draw (never cached) through the same context
+    c1 = np.zeros((h // 4, w, 4), np.float32); c2 = np.zeros((h // 4, w, 4), np.float32)
+    r1 = [ctx.draw(f, 1, w, h, c1, flags=0, mode=0, rows=(1, h // 4, 4, 1)) for f in (30, 31, 32)]
+    ctx.set_option("exact_lookahead", 0)
+    r2 = [ctx.draw(f, 1, w, h, c2, flags=0, mode=0, rows=(1, h // 4, 4, 1)) for f in (30, 31, 32)]
+    assert r1 == r2 and not bits_differ(c1, c2).any()
+    ctx.close()

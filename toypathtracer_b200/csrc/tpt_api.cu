@@ -50,6 +50,18 @@ struct tpt_context
     int fastAlphaZero = 0;
     uint32_t sceneFlags = 0;  // kScene* bits for the next tpt_set_scene    // 1: fast-mode draws whose `prev` has zero weight write alpha = 0 instead of preserving it
     int exactLanes = 0;
+    // Exact mode, one frame per call (the drop-in's DrawTest): a frame is only `height` serial RNG chains, far too few to
+    // fill the GPU (0.76 Gray/s at 720p), while 16 frames at once run at 2.6 Gray/s. With "exact_lookahead" = L > 1 a
+    // cache miss traces frames [f, f+L) in ONE launch into a per-frame colour cache and the calls for f+1 .. f+L-1 only
+    // blend their cached frame into the caller's buffer (per-frame colours do not depend on the buffer, Test.cpp:283-291):
+    // same bits, same per-frame ray counts, L frames of latency on a miss. Not used under kFlagAnimate (the scene of a
+    // future frame is not known yet); any scene, camera, size, row-range or spp change invalidates the cache.
+    int exactLookahead = 0;
+    struct LookKey { int frame0, n, width, height, row0, numRows, rowStep, spp; unsigned long long sceneGen; Camera88 cam; } look{};
+    bool lookValid = false;
+    float* dLook = nullptr; size_t lookCap = 0;
+    unsigned long long* dLookRays = nullptr; size_t lookRaysCap = 0;
+    unsigned long long sceneGen = 0;
     int registerHost = 0;
     size_t maxScratchBytes = (size_t)8 << 30;
 
@@ -197,7 +209,7 @@ void tpt_destroy(tpt_context* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->registeredPtr) cudaHostUnregister(ctx->registeredPtr);
-    cudaFree(ctx->dImage); cudaFree(ctx->dScratch); cudaFree(ctx->dRayCounters);
+    cudaFree(ctx->dImage); cudaFree(ctx->dScratch); cudaFree(ctx->dRayCounters); cudaFree(ctx->dLook); cudaFree(ctx->dLookRays);
     cudaFree(ctx->dAccum); cudaFree(ctx->dWork);
     for (int i = 0; i < 2; ++i)
     {
@@ -277,6 +289,7 @@ int tpt_set_scene(tpt_context* ctx, const void* spheres20, const void* materials
         CK(cudaEventRecord(ctx->uploadDone[slot], ctx->uploadStream), "upload event");
         ctx->curBlob = slot;
         ctx->lastBlob.swap(blob);
+        ++ctx->sceneGen;
     }
     ctx->scene.blob = ctx->dBlobs[ctx->curBlob];
     ctx->scene.layout = L;
@@ -323,6 +336,7 @@ int tpt_set_option(tpt_context* ctx, const char* key, int value)
     if (!ctx || !key) return (int)cudaErrorInvalidValue;
     if (!strcmp(key, "fast_variant")) { if (value < -1 || value > 8) return fail_msg(ctx, "fast_variant: -1 (auto), 0..8"); ctx->fastVariant = value; return 0; }
     if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 8 && value != 9 && value != 32 && (value < 64 || value > 69)) return fail_msg(ctx, "exact_lanes: 0,1,2,8,9,32,64..69"); ctx->exactLanes = value; return 0; }
+    if (!strcmp(key, "exact_lookahead")) { if (value < 0 || value > 256) return fail_msg(ctx, "exact_lookahead: 0..256"); ctx->exactLookahead = value; ctx->lookValid = false; return 0; }
     if (!strcmp(key, "register_host")) { ctx->registerHost = value ? 1 : 0; return 0; }
     if (!strcmp(key, "fast_kform")) { if (value < 0 || value > 2) return fail_msg(ctx, "fast_kform: 0..2"); ctx->fastKForm = value; return 0; }
     if (!strcmp(key, "fast_alpha_zero")) { ctx->fastAlphaZero = value ? 1 : 0; return 0; }
@@ -553,7 +567,44 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
         p.frame0 = frameCount + f;
         p.numFrames = nf;
         cudaError_t e;
-        if (mode == TPT_MODE_EXACT)
+        if (mode == TPT_MODE_EXACT && numFrames == 1 && ctx->exactLookahead > 1 && !(testFlags & TPT_FLAG_ANIMATE))
+        {
+            // frame lookahead (see tpt_context::exactLookahead)
+            tpt_context::LookKey k{};
+            k.width = width; k.height = height; k.row0 = row0; k.numRows = numRows; k.rowStep = rowStep; k.spp = ctx->spp;
+            k.sceneGen = ctx->sceneGen; k.cam = ctx->cam;
+            const tpt_context::LookKey& c = ctx->look;
+            const size_t perFrame = (size_t)numRows * width * 4;           // floats
+            const bool hit = ctx->lookValid && frameCount >= c.frame0 && frameCount < c.frame0 + c.n && c.width == k.width &&
+                             c.height == k.height && c.row0 == k.row0 && c.numRows == k.numRows && c.rowStep == k.rowStep &&
+                             c.spp == k.spp && c.sceneGen == k.sceneGen && !memcmp(&c.cam, &k.cam, sizeof(Camera88));
+            if (!hit)
+            {
+                size_t L = (size_t)ctx->exactLookahead;
+                const size_t fit = ctx->maxScratchBytes / (perFrame * 4);
+                if (L > fit) L = fit < 1 ? 1 : fit;
+                int r = ensure(ctx, (void**)&ctx->dLook, &ctx->lookCap, L * perFrame * 4, "cudaMalloc lookahead cache");
+                if (r) return r;
+                r = ensure(ctx, (void**)&ctx->dLookRays, &ctx->lookRaysCap, L * sizeof(unsigned long long), "cudaMalloc lookahead counters");
+                if (r) return r;
+                CK(cudaMemsetAsync(ctx->dLookRays, 0, L * sizeof(unsigned long long), stream), "zero lookahead counters");
+                DrawParams pl = p;
+                pl.frame0 = frameCount; pl.numFrames = (int)L; pl.scratch = ctx->dLook; pl.rayCounter = ctx->dLookRays;
+                e = launch_exact(pl, scene, ctx->exactLanes, stream, /*resolve*/ L == 1);
+                if (e != cudaSuccess) return fail(ctx, e, "kernel launch");
+                ctx->lastLaunches += 1;
+                k.frame0 = frameCount; k.n = (int)L;
+                ctx->look = k; ctx->lookValid = L > 1;
+                if (L == 1) { CK(cudaMemcpyAsync(ctx->dRayCounters, ctx->dLookRays, 8, cudaMemcpyDeviceToDevice, stream), "counter copy"); continue; }
+            }
+            const int i = frameCount - ctx->look.frame0;
+            DrawParams pr = p;
+            pr.frame0 = frameCount; pr.numFrames = 1; pr.scratch = ctx->dLook + (size_t)i * perFrame;
+            e = launch_resolve_exact(pr, stream);
+            ctx->lastLaunches += 1;
+            CK(cudaMemcpyAsync(ctx->dRayCounters, ctx->dLookRays + i, 8, cudaMemcpyDeviceToDevice, stream), "counter copy");
+        }
+        else if (mode == TPT_MODE_EXACT)
         {
             p.rayCounter = ctx->dRayCounters + f;
             p.scratch = nullptr;

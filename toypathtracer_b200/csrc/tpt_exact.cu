@@ -401,7 +401,14 @@ cudaError_t launch_refgpu_exact(const DrawParams& p, const SceneDev& sc, int num
     return launch_refgpu_t<true>(p, sc, numSMs, stream);
 }
 
-cudaError_t launch_exact(const DrawParams& p, const SceneDev& sc, int lanes, cudaStream_t stream)
+cudaError_t launch_resolve_exact(const DrawParams& p, cudaStream_t stream)
+{
+    const long long n = (long long)p.numRows * p.width;
+    k_resolve_exact<<<(int)((n + 255) / 256), 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_exact(const DrawParams& p, const SceneDev& sc, int lanes, cudaStream_t stream, bool resolve)
 {
     const long long totalChains = (long long)p.numRows * p.numFrames;
     if (lanes <= 0)
@@ -432,12 +439,7 @@ cudaError_t launch_exact(const DrawParams& p, const SceneDev& sc, int lanes, cud
     default: return cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return e;
-    if (p.numFrames > 1)
-    {
-        const long long n = (long long)p.numRows * p.width;
-        k_resolve_exact<<<(int)((n + 255) / 256), 256, 0, stream>>>(p);
-        e = cudaGetLastError();
-    }
+    if (p.numFrames > 1 && resolve) e = launch_resolve_exact(p, stream);
     return e;
 }
 
