@@ -126,6 +126,12 @@ int tpt_last_launch_count(tpt_context* ctx);
  * presentation step of the reference shells (Cpp/Windows/PixelShader.hlsl:1-15). dst = width*height*4 bytes. */
 int tpt_tonemap_srgb8(tpt_context* ctx, const float* image, int imageOnDevice, int width, int height,
                       unsigned char* dst, int dstOnDevice, void* cudaStream);
+/* The reference's other two 8-bit conversions in the same pass: transfer 0 = the above, 1 = min(sqrtf(x)*255, 255), the
+ * WebAssembly shell's cheap gamma (Cpp/Emscripten/main.cpp:67-79, which also flips Y), 2 = the C# TGA writer's
+ * LinearToSRGB with its 255.9 truncation (Cs/Program.cs:34-68: bgr = 1, flipY = 0 — TGA rows are bottom-up like the
+ * backbuffer's). */
+int tpt_tonemap_rgba8(tpt_context* ctx, const float* image, int imageOnDevice, int width, int height,
+                      unsigned char* dst, int dstOnDevice, int transfer, int bgr, int flipY, void* cudaStream);
 
 /* Multi-GPU, one process per GPU: device memory that another process's kernels can write into directly over
  * NVLink/NVSwitch (CUDA IPC). The root rank allocates the image and exports a 64-byte handle; every other rank

@@ -35,7 +35,7 @@ def test_golden_vectors(gpu_ctx):
     g = np.load(os.path.join(GOLD, "ref_192x108_f0-3.npz"))
     sph, mats, cam, em = golden_scene()
     gpu_ctx.set_scene(sph, mats, cam, em)
-    for lanes in (32, 8, 9, 1, 2, 64, 65, 0):
+    for lanes in (32, 8, 9, 1, 2, 64, 65, 70, 0):
         gpu_ctx.set_option("exact_lanes", lanes)
         # frame by frame (numFrames = 1: blend fused into the trace kernel)
         buf = np.zeros((108, 192, 4), np.float32)
@@ -140,7 +140,7 @@ def test_runtime_scenes_against_restatement(libs, gpu_ctx, oracle):
     for (sph, mats, cam, w, h) in cases:
         gpu_ctx.set_scene(sph, mats, cam, None)
         obuf, orays, pads = oracle.orc_render(sph, mats, cam, w, h, 0, 2, flags=2)
-        for lanes in (32, 1, 64, 65):
+        for lanes in (32, 1, 64, 65, 70):
             gpu_ctx.set_option("exact_lanes", lanes)
             buf = np.zeros((h, w, 4), np.float32)
             total, pf = gpu_ctx.draw(0, 2, w, h, buf, flags=2, mode=0, per_frame=True)
@@ -201,7 +201,7 @@ def test_odd_sizes_and_single_row(gpu_ctx, oracle):
         cam = tpt.make_camera((0, 2, 3), (0, 0, 0), (0, 1, 0), 60, w / h, 0.02, 3)
         gpu_ctx.set_scene(sph, mats, cam, em)
         obuf, orays, pads = oracle.orc_render(sph, mats, cam, w, h, 2, 2, flags=2)
-        for lanes in (32, 8, 1, 64, 65):
+        for lanes in (32, 8, 1, 64, 65, 70):
             gpu_ctx.set_option("exact_lanes", lanes)
             buf = np.zeros((h, w, 4), np.float32)
             total, pf = gpu_ctx.draw(2, 2, w, h, buf, flags=2, mode=0, per_frame=True)

@@ -99,6 +99,23 @@ def test_tonemap(gpu_ctx):
     assert (out[..., 3] == 255).all()
 
 
+def test_tonemap_other_shells_conversions(gpu_ctx):
+    """The WebAssembly shell's sqrt gamma with Y flip (Emscripten/main.cpp:67-79) and the C# TGA writer's BGR
+    LinearToSRGB with its 255.9 truncation (Cs/Program.cs:34-68), against numpy restatements of those lines."""
+    rng = np.random.default_rng(5)
+    img = (rng.random((9, 16, 4), dtype=np.float32) * 1.6).astype(np.float32)
+    img[0, 0, :3] = (0.0, 1.0, 4.0)
+    out = gpu_ctx.tonemap_rgba8(img, 16, 9, transfer=1, bgr=False, flip_y=True)
+    ref = np.minimum(np.sqrt(img[::-1, :, :3]) * np.float32(255), np.float32(255.0)).astype(np.uint8)
+    assert (out[..., :3] == ref).all() and (out[..., 3] == 255).all()
+    out = gpu_ctx.tonemap_rgba8(img, 16, 9, transfer=2, bgr=True, flip_y=False)
+    x = np.maximum(img[..., :3], 0)
+    x = np.maximum(np.float32(1.055) * np.power(x, np.float32(0.416666667)) - np.float32(0.055), 0).astype(np.float32)
+    ref = np.minimum((x * np.float32(255.9)).astype(np.uint32), 255).astype(np.int32)[..., ::-1]
+    assert np.abs(out[..., :3].astype(np.int32) - ref).max() <= 1          # __powf vs powf: at most one code at a truncation edge
+    assert (np.abs(out[..., :3].astype(np.int32) - ref) != 0).mean() < 0.02
+
+
 def test_host_band_pipelining_equals_single_launch(gpu_ctx):
     """Host-buffer draws overlap the D2H with tracing, either (a) with ONE kernel that publishes per-band completion
     counters the copy stream waits on (cuStreamWaitValue32, `host_progress`), or (b) with one launch per row band on its

@@ -71,6 +71,7 @@ def _load_lib():
     L.tpt_last_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]; L.tpt_last_kernel_ms.restype = ci
     L.tpt_last_launch_count.argtypes = [vp]; L.tpt_last_launch_count.restype = ci
     L.tpt_tonemap_srgb8.argtypes = [vp, vp, ci, ci, ci, vp, ci, vp]; L.tpt_tonemap_srgb8.restype = ci
+    L.tpt_tonemap_rgba8.argtypes = [vp, vp, ci, ci, ci, vp, ci, ci, ci, ci, vp]; L.tpt_tonemap_rgba8.restype = ci
     L.tpt_debug_libm.argtypes = [vp, ci, vp, vp, cll]; L.tpt_debug_libm.restype = ci
     cull = ctypes.c_ulonglong
     L.tpt_mem_alloc.argtypes = [vp, cull, ctypes.POINTER(vp)]; L.tpt_mem_alloc.restype = ci
@@ -239,6 +240,16 @@ class Context:
         out = np.empty((height, width, 4), np.uint8)
         self._check(self._L.tpt_tonemap_srgb8(self._h, ctypes.c_void_p(addr), 1 if on_dev else 0, width, height,
                                               out.ctypes.data, 0, None), "tpt_tonemap_srgb8")
+        return out
+
+    def tonemap_rgba8(self, image, width: int, height: int, transfer: int = 0, bgr: bool = False, flip_y: bool = True) -> np.ndarray:
+        """transfer 0: LinearToSRGB (PixelShader.hlsl), 1: sqrt gamma (Emscripten/main.cpp:67-79), 2: the C# TGA writer's
+        (Cs/Program.cs:34-68; use bgr=True, flip_y=False for its byte layout)."""
+        addr, on_dev, _keep = _as_ptr(image)
+        out = np.empty((height, width, 4), np.uint8)
+        self._check(self._L.tpt_tonemap_rgba8(self._h, ctypes.c_void_p(addr), 1 if on_dev else 0, width, height,
+                                              out.ctypes.data, 0, transfer, 1 if bgr else 0, 1 if flip_y else 0, None),
+                    "tpt_tonemap_rgba8")
         return out
 
 

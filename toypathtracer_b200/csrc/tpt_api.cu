@@ -125,20 +125,27 @@ __global__ void k_accumulate_rays(const unsigned long long* perFrame, int n, uns
     accum[1] = s;
 }
 
-// LinearToSRGB of the reference's presentation pass (Cpp/Windows/PixelShader.hlsl:1-5) + Y flip (row 0 of the
-// float image is the bottom, Cpp/Emscripten/main.cpp:67-79), 4 bytes per pixel.
-__global__ void k_tonemap_srgb8(const float4* __restrict__ img, int width, int height, uchar4* __restrict__ dst)
+// The reference's three presentation conversions of the linear float image to 8 bits per channel (row f.1):
+//   transfer 0  LinearToSRGB of the D3D11/Metal presentation pass (Cpp/Windows/PixelShader.hlsl:1-15), rounded
+//   transfer 1  min(sqrtf(x) * 255, 255) truncated — the WebAssembly shell's cheap gamma (Cpp/Emscripten/main.cpp:67-79)
+//   transfer 2  the C# TGA writer's LinearToSRGB: min((uint)(x * 255.9f), 255) (Cs/Program.cs:61-67)
+// flipY: row 0 of the float image is the bottom (the Emscripten shell flips, the TGA writer does not: TGA is bottom-up);
+// bgr: TGA channel order (Cs/Program.cs:36-41).
+__global__ void k_tonemap_rgba8(const float4* __restrict__ img, int width, int height, uchar4* __restrict__ dst, int transfer, int bgr, int flipY)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= width * height) return;
     const int x = idx % width, y = idx / width;
-    float4 c = ld_stream_f4(reinterpret_cast<const float*>(img + (size_t)(height - 1 - y) * width + x));
-    auto enc = [](float v) {
+    float4 c = ld_stream_f4(reinterpret_cast<const float*>(img + (size_t)(flipY ? height - 1 - y : y) * width + x));
+    auto enc = [transfer](float v) -> unsigned char {
+        if (transfer == 1) return (unsigned char)fminf(__fsqrt_rn(v) * 255.0f, 255.0f);
         v = fmaxf(v, 0.0f);
         v = fmaxf(1.055f * __powf(v, 0.416666667f) - 0.055f, 0.0f);
+        if (transfer == 2) { unsigned u = (unsigned)(v * 255.9f); return (unsigned char)(u < 255u ? u : 255u); }
         return (unsigned char)(fminf(v, 1.0f) * 255.0f + 0.5f);
     };
-    dst[idx] = make_uchar4(enc(c.x), enc(c.y), enc(c.z), 255);
+    const unsigned char r = enc(c.x), g = enc(c.y), b = enc(c.z);
+    dst[idx] = bgr ? make_uchar4(b, g, r, 255) : make_uchar4(r, g, b, 255);
 }
 } // namespace tpt
 
@@ -335,7 +342,7 @@ int tpt_set_option(tpt_context* ctx, const char* key, int value)
 {
     if (!ctx || !key) return (int)cudaErrorInvalidValue;
     if (!strcmp(key, "fast_variant")) { if (value < -1 || value > 8) return fail_msg(ctx, "fast_variant: -1 (auto), 0..8"); ctx->fastVariant = value; return 0; }
-    if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 8 && value != 9 && value != 32 && (value < 64 || value > 69)) return fail_msg(ctx, "exact_lanes: 0,1,2,8,9,32,64..69"); ctx->exactLanes = value; return 0; }
+    if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 8 && value != 9 && value != 32 && (value < 64 || value > 70)) return fail_msg(ctx, "exact_lanes: 0,1,2,8,9,32,64..70"); ctx->exactLanes = value; return 0; }
     if (!strcmp(key, "exact_lookahead")) { if (value < 0 || value > 256) return fail_msg(ctx, "exact_lookahead: 0..256"); ctx->exactLookahead = value; ctx->lookValid = false; return 0; }
     if (!strcmp(key, "register_host")) { ctx->registerHost = value ? 1 : 0; return 0; }
     if (!strcmp(key, "fast_kform")) { if (value < 0 || value > 2) return fail_msg(ctx, "fast_kform: 0..2"); ctx->fastKForm = value; return 0; }
@@ -696,10 +703,11 @@ int tpt_last_kernel_ms(tpt_context* ctx, float* outMs)
 
 int tpt_last_launch_count(tpt_context* ctx) { return ctx ? ctx->lastLaunches : 0; }
 
-int tpt_tonemap_srgb8(tpt_context* ctx, const float* image, int imageOnDevice, int width, int height,
-                      unsigned char* dst, int dstOnDevice, void* cudaStreamArg)
+int tpt_tonemap_rgba8(tpt_context* ctx, const float* image, int imageOnDevice, int width, int height,
+                      unsigned char* dst, int dstOnDevice, int transfer, int bgr, int flipY, void* cudaStreamArg)
 {
     if (!ctx || !image || !dst || width <= 0 || height <= 0) return (int)cudaErrorInvalidValue;
+    if (transfer < 0 || transfer > 2) return fail_msg(ctx, "tpt_tonemap_rgba8: transfer 0..2");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     cudaStream_t stream = cudaStreamArg ? (cudaStream_t)cudaStreamArg : ctx->stream;
     const size_t inBytes = (size_t)width * height * 16, outBytes = (size_t)width * height * 4;
@@ -719,7 +727,7 @@ int tpt_tonemap_srgb8(tpt_context* ctx, const float* image, int imageOnDevice, i
         dOut = (unsigned char*)ctx->dScratch;
     }
     const int n = width * height;
-    k_tonemap_srgb8<<<(n + 255) / 256, 256, 0, stream>>>((const float4*)dIn, width, height, (uchar4*)dOut);
+    k_tonemap_rgba8<<<(n + 255) / 256, 256, 0, stream>>>((const float4*)dIn, width, height, (uchar4*)dOut, transfer, bgr ? 1 : 0, flipY ? 1 : 0);
     CK(cudaGetLastError(), "tonemap launch");
     if (!dstOnDevice)
     {
@@ -727,6 +735,12 @@ int tpt_tonemap_srgb8(tpt_context* ctx, const float* image, int imageOnDevice, i
         CK(cudaStreamSynchronize(stream), "stream sync");
     }
     return 0;
+}
+
+int tpt_tonemap_srgb8(tpt_context* ctx, const float* image, int imageOnDevice, int width, int height,
+                      unsigned char* dst, int dstOnDevice, void* cudaStreamArg)
+{
+    return tpt_tonemap_rgba8(ctx, image, imageOnDevice, width, height, dst, dstOnDevice, 0, 0, 1, cudaStreamArg);
 }
 
 int tpt_mem_alloc(tpt_context* ctx, unsigned long long bytes, void** outDevPtr)

@@ -358,6 +358,275 @@ k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneB
     }
 }
 
+// ---- cluster form of the split kernel: the two roles on DIFFERENT SMs ---------------------------------------------------------
+// ncu on k_trace_exact_split: 17 % of the stall samples are `no_instructions`, i-cache hit rate 82 % (99.7 % for the path
+// warp alone) — path code and shade code together (~54 KB) do not fit the instruction cache of an SM that hosts both
+// roles, and the path warp, whose latency IS the frame time, pays for it. Here a thread-block CLUSTER of two CTAs, each
+// sized to own its SM, splits the roles by SM: CTA 0 runs kCPathWarps path warps (each pulls chains from a global counter),
+// CTA 1 runs the kCH shade warps of each of them. The event rings and the `full` barriers live in the shade CTA's shared
+// memory and are written/arrived over DSMEM (st.shared::cluster / mbarrier.arrive.release.cluster), the `empty` barriers
+// in the path CTA's; a chain starts with an XE_BEGIN event and the kernel ends with XE_QUIT.
+constexpr int kCPathWarps = 10;
+constexpr int kCH = 2;
+constexpr int kCThreads = 32 * kCPathWarps * kCH;
+enum { XE_BEGIN = 4, XE_QUIT = 5 };
+
+struct ClusterShared
+{
+    uint64_t fullBar[kCPathWarps][kCH][kRingDepth];       // used in CTA 1 (waited on locally, arrived remotely)
+    uint64_t emptyBar[kCPathWarps][kCH][kRingDepth];      // used in CTA 0
+    XEventSlot ring[kCPathWarps][kCH][kRingDepth];        // CTA 1
+    float pixRes[kCPathWarps][kPixSlots][kSplitMaxSpp][3];
+    unsigned pixCnt[kCPathWarps][kPixSlots];
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t map_to_cta(const void* localSmem, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(localSmem)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t clusterAddr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(clusterAddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_C;\n"
+        "WAIT_LOOP_C:\n"
+        "nanosleep.u32 128;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@!p bra WAIT_LOOP_C;\n"
+        "DONE_C:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(100000u) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t clusterAddr, float4 v)
+{
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(clusterAddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCThreads, 1)
+k_trace_exact_cluster(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights, uint32_t stagedBytes)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ ClusterShared cs;
+    stage_blob(smem, blob, stagedBytes, &bar);
+    for (int i = threadIdx.x; i < kCPathWarps * kCH * kRingDepth; i += blockDim.x)
+    {
+        mbar_init(&cs.fullBar[0][0][0] + i, 1);
+        mbar_init(&cs.emptyBar[0][0][0] + i, 1);
+    }
+    if (threadIdx.x < kCPathWarps * kPixSlots) (&cs.pixCnt[0][0])[threadIdx.x] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                   // both CTAs' barriers exist before anyone touches them
+    SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t rank = cluster_ctarank();
+    const long long totalChains = (long long)p.numRows * p.numFrames;
+    const int spp = p.spp;
+
+    if (rank == 0 && warp < kCPathWarps)
+    {
+        // ---- PATH warp `warp`
+        GroupHitter<1, 32> hitter;
+        hitter.sub = lane; hitter.mask = 0xffffffffu;
+        uint32_t seq[kCH];
+#pragma unroll
+        for (int h = 0; h < kCH; ++h) seq[h] = 0;
+        auto emit_to = [&](int h, int type, int mid, V3 a, V3 b, V3 c, uint32_t erng) {
+            uint32_t sq = 0;
+#pragma unroll
+            for (int hh = 0; hh < kCH; ++hh) if (hh == h) sq = seq[hh];
+            const uint32_t slot = sq % kRingDepth, phase = (sq / kRingDepth) & 1u;
+            mbar_wait_cluster(&cs.emptyBar[warp][h][slot], phase ^ 1u);
+            if (lane == 0)
+            {
+                const uint32_t e = map_to_cta(&cs.ring[warp][h][slot], 1);
+                st_cluster_f4(e, make_float4(a.x, a.y, a.z, __int_as_float(type | (mid << 3))));
+                st_cluster_f4(e + 16, make_float4(b.x, b.y, b.z, __uint_as_float(erng)));
+                st_cluster_f4(e + 32, make_float4(c.x, c.y, c.z, 0.0f));
+                mbar_arrive_remote(map_to_cta(&cs.fullBar[warp][h][slot], 1));
+            }
+#pragma unroll
+            for (int hh = 0; hh < kCH; ++hh) if (hh == h) seq[hh] = sq + 1;
+        };
+        const V3 zero = v3(0, 0, 0);
+        for (;;)
+        {
+            unsigned chainU = 0;
+            if (lane == 0) chainU = atomicAdd(p.workCounter, 1u);
+            chainU = __shfl_sync(0xffffffffu, chainU, 0);
+            if ((long long)chainU >= totalChains) break;
+            const int ri = (int)(chainU / (unsigned)p.numFrames), fi = (int)(chainU % (unsigned)p.numFrames);
+            const int y = p.row0 + ri * p.rowStep, frame = p.frame0 + fi;
+#pragma unroll
+            for (int h = 0; h < kCH; ++h) emit_to(h, XE_BEGIN, (int)chainU, zero, zero, zero, 0u);
+            uint32_t rng = row_seed(y, frame);
+            unsigned rc = 0;
+            uint32_t k = 0;
+            for (int x = 0; x < p.width; ++x)
+                for (int s = 0; s < spp; ++s, ++k)
+                {
+                    const int h = (int)(k % (uint32_t)kCH);
+                    xpath_sample(sc, p.cam, x, y, p.invWidth, p.invHeight, rng, rc, hitter,
+                                 [&](int type, int mid, V3 a, V3 b, V3 c, uint32_t erng) { emit_to(h, type, mid, a, b, c, erng); });
+                }
+            if (lane == 0) atomicAdd(p.rayCounter + fi, (unsigned long long)rc);
+        }
+#pragma unroll
+        for (int h = 0; h < kCH; ++h) emit_to(h, XE_QUIT, 0, zero, zero, zero, 0u);
+    }
+    else if (rank == 1)
+    {
+        // ---- SHADE warp: serves path warp pw, samples k with k % kCH == h
+        const int pw = warp / kCH, h = warp % kCH;
+        const int grp = lane >> 4;
+        GroupHitter<2, 16> hitter;
+        hitter.sub = lane & 15; hitter.mask = 0xffffu << (grp * 16);
+        const float invSpp = M<2>::div_(1.0f, (float)spp);
+        uint32_t seq = 0, k = 0, pixBase = 0, chainsSeen = 0;
+        int ri = 0, fi = 0, y = 0, frame = 0;
+        float lerpFac = 0.0f, oneMinus = 1.0f;
+        size_t imgRow = 0;
+        XShade sh;
+        xshade_begin(sh);
+
+        auto lights = [&](int mid, V3 pos, V3 normal, V3 rdir, V3 albedo, uint32_t rng) -> V3 {
+            V3 lightE = v3(0, 0, 0);
+            int myJ = -1, kk = 0;
+            uint32_t myRng = 0;
+            auto run_batch = [&]() {
+                V3 contrib = v3(0, 0, 0);
+                bool reached = false;
+                if (myJ >= 0)
+                {
+                    const LightRec Lr = sc.lights[myJ];
+                    V3 l;
+                    sample_light<2>(Lr, pos, normal, rdir, albedo, myRng, l, contrib);
+                    float ts;
+                    reached = hitter.hit(sc, pos, l, TPT_MIN_T, TPT_MAX_T, ts) == Lr.id;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int g = 0; g < 2; ++g)
+                {
+                    const bool r = __shfl_sync(0xffffffffu, reached ? 1 : 0, g * 16) != 0;
+                    const V3 cg = v3(__shfl_sync(0xffffffffu, contrib.x, g * 16), __shfl_sync(0xffffffffu, contrib.y, g * 16),
+                                     __shfl_sync(0xffffffffu, contrib.z, g * 16));
+                    if (r) lightE = lightE + cg;
+                }
+                myJ = -1;
+            };
+            for (int j = 0; j < sc.nLights; ++j)
+            {
+                if (sc.lights[j].id == mid) continue;
+                if ((kk & 1) == grp) { myJ = j; myRng = rng; }
+                XorShift32(rng); XorShift32(rng);
+                if ((++kk & 1) == 0) run_batch();
+            }
+            if (kk & 1) run_batch();
+            return lightE;
+        };
+
+        for (;;)
+        {
+            const uint32_t slot = seq % kRingDepth, phase = (seq / kRingDepth) & 1u;
+            mbar_wait_cluster(&cs.fullBar[pw][h][slot], phase);
+            const XEventSlot& e = cs.ring[pw][h][slot];
+            const float4 q0 = e.q0, q1 = e.q1, q2 = e.q2;
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(map_to_cta(&cs.emptyBar[pw][h][slot], 0));
+            ++seq;
+            const int tm = __float_as_int(q0.w), type = tm & 7, mid = tm >> 3;
+            if (type == XE_QUIT) break;
+            if (type == XE_BEGIN)
+            {
+                pixBase = chainsSeen++ * (uint32_t)p.width;   // pixel slots are indexed by a running pixel number across chains
+                ri = mid / p.numFrames; fi = mid % p.numFrames;
+                y = p.row0 + ri * p.rowStep; frame = p.frame0 + fi;
+                lerpFac = lerp_fac(frame, p.flags); oneMinus = 1.0f - lerpFac;
+                imgRow = (size_t)(p.packed ? ri : y) * p.width;
+                k = (uint32_t)h;
+                xshade_begin(sh);
+                continue;
+            }
+            V3 result;
+            if (!xshade_event(sc, sh, type, mid, v3(q0.x, q0.y, q0.z), v3(q1.x, q1.y, q1.z), v3(q2.x, q2.y, q2.z),
+                              __float_as_uint(q1.w), lights, result)) continue;
+            // sample k of the chain finished
+            const int x = (int)(k / (uint32_t)spp), s = (int)(k - (uint32_t)x * (uint32_t)spp);
+            const int ps = (int)((pixBase + (uint32_t)x) % (uint32_t)kPixSlots);
+            unsigned old = 0;
+            if (lane == 0)
+            {
+                cs.pixRes[pw][ps][s][0] = result.x; cs.pixRes[pw][ps][s][1] = result.y; cs.pixRes[pw][ps][s][2] = result.z;
+                __threadfence_block();
+                old = atomicInc(&cs.pixCnt[pw][ps], (unsigned)spp - 1u);
+            }
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (old == (unsigned)spp - 1u && lane == 0)
+            {
+                __threadfence_block();
+                V3 col = v3(0, 0, 0);
+                for (int t = 0; t < spp; ++t)
+                    col = col + v3(((volatile float*)cs.pixRes[pw][ps][t])[0], ((volatile float*)cs.pixRes[pw][ps][t])[1], ((volatile float*)cs.pixRes[pw][ps][t])[2]);
+                col = col * invSpp;
+                if (p.numFrames == 1)
+                {
+                    float4* px = reinterpret_cast<float4*>(p.image + (imgRow + x) * 4);
+                    float4 prev = *px;
+                    prev.x = prev.x * lerpFac + col.x * oneMinus;
+                    prev.y = prev.y * lerpFac + col.y * oneMinus;
+                    prev.z = prev.z * lerpFac + col.z * oneMinus;
+                    *px = prev;
+                }
+                else
+                {
+                    float4* px = reinterpret_cast<float4*>(p.scratch) + ((size_t)fi * p.numRows + ri) * p.width + x;
+                    *px = make_float4(col.x, col.y, col.z, 0.0f);
+                }
+            }
+            __syncwarp();
+            k += (uint32_t)kCH;
+            xshade_begin(sh);
+        }
+    }
+    // nobody leaves while the partner CTA may still address this CTA's shared memory
+    __syncthreads();
+    cluster_sync_all();
+}
+
+static cudaError_t launch_exact_cluster(const DrawParams& p, const SceneDev& sc, cudaStream_t stream)
+{
+    // one CTA per SM: ask for more than half of an SM's shared memory
+    const size_t wantDyn = 118 * 1024;
+    const size_t dyn = sc.stagedBytes > wantDyn ? sc.stagedBytes : wantDyn;
+    cudaError_t e = cudaFuncSetAttribute(k_trace_exact_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(p.workCounter, 0, sizeof(unsigned int), stream);
+    if (e != cudaSuccess) return e;
+    const long long totalChains = (long long)p.numRows * p.numFrames;
+    int dev = 0, numSMs = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev);
+    long long clusters = numSMs / 2;
+    const long long need = (totalChains + kCPathWarps - 1) / kCPathWarps;
+    if (clusters > need) clusters = need;
+    k_trace_exact_cluster<<<(unsigned)(2 * clusters), kCThreads, dyn, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes);
+    return cudaGetLastError();
+}
+
 template <int H, int DRY = 0>
 static cudaError_t launch_exact_split_t(const DrawParams& p, const SceneDev& sc, cudaStream_t stream)
 {
@@ -429,6 +698,10 @@ cudaError_t launch_exact(const DrawParams& p, const SceneDev& sc, int lanes, cud
     case 9: e = launch_exact_flat_t<8>(p, sc, stream); break;        // flat form with 8 lanes per chain: measured 2x SLOWER than
                                                                      // the nested form at 11 520 chains (221 vs 111 ms), comparison only
     case 32: e = launch_exact_t<32>(p, sc, stream, block); break;
+    case 70:                                                         // split kernel, roles on different SMs (2-CTA clusters)
+        if (p.spp > kSplitMaxSpp || totalChains >= (1LL << 27)) return cudaErrorInvalidValue;
+        e = launch_exact_cluster(p, sc, stream);
+        break;
     case 64: case 65: case 66: case 67: case 68: case 69:            // split kernel: path warp + 1..4 shade warps per chain
         if (p.spp > kSplitMaxSpp || totalChains > 0x7fffffffLL) return cudaErrorInvalidValue;
         e = lanes == 64 ? launch_exact_split_t<1>(p, sc, stream) : lanes == 65 ? launch_exact_split_t<2>(p, sc, stream)

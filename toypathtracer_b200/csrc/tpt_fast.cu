@@ -1483,7 +1483,7 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
         const int simd = (sc.count + 3) / 4 * 4;
         const int kform = !sc.kformOk ? 0 : (sc.kformMode == 1 || simd > 1024 ? 1 : 2);
         auto kern = variant == 3 ? (kform == 2 ? k_fast_queue<TPT_QUEUE_MINB, 2> : kform == 1 ? k_fast_queue<TPT_QUEUE_MINB, 1> : k_fast_queue<TPT_QUEUE_MINB, 0>)
-                                 : (kform == 2 ? k_fast_queue<8, 2> : kform == 1 ? k_fast_queue<8, 1> : k_fast_queue<8, 0>);
+                                 : (kform == 2 ? k_fast_queue<7, 2> : kform == 1 ? k_fast_queue<7, 1> : k_fast_queue<7, 0>);
         const size_t dyn3 = kform == 2 ? ((sc.stagedBytes + 127u) & ~127u) + (size_t)simd * 16 : sc.stagedBytes;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn3);
         if (e != cudaSuccess) return e;
