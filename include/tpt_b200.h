@@ -71,7 +71,9 @@ int tpt_set_spp(tpt_context* ctx, int spp);
  * (0 auto; 64..67 = split kernel: one PATH warp per (frame,row) chain walks the RNG stream, 1..4 SHADE warps do the light
  * sampling / fold / blend off the critical path (auto for <= 1600 chains); 32 or 8 lanes per chain as nested loops; 1 = one
  * thread per chain as a flat one-sweep-per-step state machine (auto for >= 100 000 chains); 2 = one thread per chain
- * nested, 9 = 8 lanes flat: measured slower, kept for comparison; 68/69 timing probes), "register_host" (1: page-lock the caller's host backbuffer with cudaHostRegister the first
+ * nested, 9 = 8 lanes flat: measured slower, kept for comparison; 68/69 timing probes; 70 = the split kernel as 2-CTA
+ * clusters with the roles on different SMs and the rings over DSMEM, 71 = shade warps calling out-of-line libm: both measured
+ * slower, kept for comparison), "register_host" (1: page-lock the caller's host backbuffer with cudaHostRegister the first
  * time it is seen so both copies run at full PCIe rate; only safe when the buffer outlives the context, as a
  * reference shell's does; default 0 — buffers that are already pinned are detected by CUDA on their own), "host_bands" (1..8, default 3:
  * host-buffer fast draws are split into row bands on separate streams so the D2H of one band overlaps the tracing of

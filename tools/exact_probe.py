@@ -7,7 +7,7 @@ import toypathtracer_b200 as tpt
 
 ctx = tpt.Context(0)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); sh = stream.cuda_stream
-cases = [(1280, 720, 1, (65, 70)), (3840, 2160, 1, (32, 70)), (1280, 720, 4, (32, 70))]
+cases = [(1280, 720, 1, (65, 72, 73, 69, 74))]
 if len(sys.argv) > 1:
     cases = cases[: int(sys.argv[1])]
 for (w, h, nf, lanes_list) in cases:

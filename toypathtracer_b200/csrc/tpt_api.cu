@@ -342,7 +342,7 @@ int tpt_set_option(tpt_context* ctx, const char* key, int value)
 {
     if (!ctx || !key) return (int)cudaErrorInvalidValue;
     if (!strcmp(key, "fast_variant")) { if (value < -1 || value > 8) return fail_msg(ctx, "fast_variant: -1 (auto), 0..8"); ctx->fastVariant = value; return 0; }
-    if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 8 && value != 9 && value != 32 && (value < 64 || value > 70)) return fail_msg(ctx, "exact_lanes: 0,1,2,8,9,32,64..70"); ctx->exactLanes = value; return 0; }
+    if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 8 && value != 9 && value != 32 && (value < 64 || value > 71)) return fail_msg(ctx, "exact_lanes: 0,1,2,8,9,32,64..71"); ctx->exactLanes = value; return 0; }
     if (!strcmp(key, "exact_lookahead")) { if (value < 0 || value > 256) return fail_msg(ctx, "exact_lookahead: 0..256"); ctx->exactLookahead = value; ctx->lookValid = false; return 0; }
     if (!strcmp(key, "register_host")) { ctx->registerHost = value ? 1 : 0; return 0; }
     if (!strcmp(key, "fast_kform")) { if (value < 0 || value > 2) return fail_msg(ctx, "fast_kform: 0..2"); ctx->fastKForm = value; return 0; }

@@ -184,7 +184,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 
 constexpr int split_block_threads(int H) { return H <= 3 ? 128 : 32 * (1 + H); }   // 4-warp CTAs: one role per SM sub-partition
 
-template <int H, int DRY = 0>     // DRY: timing probes — 1 = shade warps only drain the rings, 2 = everything but the light sampling
+template <int H, int DRY = 0, int SMODE = 1>     // DRY: timing probes — 1 = shade warps only drain the rings, 2 = everything but the light sampling;
+                                                 // SMODE: arithmetic flavour of the shade warps (1 = inlined: 882 Mray/s at 720p; 2 = shared out-of-line sqrt/div/libm: 780)
 __global__ void __launch_bounds__(split_block_threads(H))
 k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights, uint32_t stagedBytes)
 {
@@ -205,7 +206,7 @@ k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneB
     __syncthreads();
     SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;     // (rotating the roles over the 4 sub-partitions: no effect, measured)
     const long long chain = blockIdx.x;
     // same chain order as k_trace_exact: consecutive chains = the same row in consecutive frames
     const int ri = (int)(chain / p.numFrames), fi = (int)(chain % p.numFrames);
@@ -256,11 +257,11 @@ k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneB
     const int h = warp - 1;
     if (h >= H) return;                                          // padding warp of the 4-warp CTA
     const int grp = lane >> 4;                                   // half-warp = one light
-    GroupHitter<2, 16> hitter;                                   // shade warps: out-of-line sqrt/div/libm (small code)
+    GroupHitter<SMODE, 16> hitter;
     hitter.sub = lane & 15; hitter.mask = 0xffffu << (grp * 16);
     const float lerpFac = lerp_fac(frame, p.flags);
     const float oneMinus = 1.0f - lerpFac;
-    const float invSpp = M<2>::div_(1.0f, (float)spp);
+    const float invSpp = M<SMODE>::div_(1.0f, (float)spp);
     const size_t imgRow = (size_t)(p.packed ? ri : y) * p.width;
     uint32_t seq = 0;
 
@@ -276,7 +277,7 @@ k_trace_exact_split(DrawParams p, const unsigned char* __restrict__ blob, SceneB
             {
                 const LightRec Lr = sc.lights[myJ];
                 V3 l;
-                sample_light<2>(Lr, pos, normal, rdir, albedo, myRng, l, contrib);
+                sample_light<SMODE>(Lr, pos, normal, rdir, albedo, myRng, l, contrib);
                 float ts;
                 reached = hitter.hit(sc, pos, l, TPT_MIN_T, TPT_MAX_T, ts) == Lr.id;
             }
@@ -627,11 +628,11 @@ static cudaError_t launch_exact_cluster(const DrawParams& p, const SceneDev& sc,
     return cudaGetLastError();
 }
 
-template <int H, int DRY = 0>
+template <int H, int DRY = 0, int SMODE = 1>
 static cudaError_t launch_exact_split_t(const DrawParams& p, const SceneDev& sc, cudaStream_t stream)
 {
     const long long totalChains = (long long)p.numRows * p.numFrames;
-    auto kern = k_trace_exact_split<H, DRY>;
+    auto kern = k_trace_exact_split<H, DRY, SMODE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc.stagedBytes);
     if (e != cudaSuccess) return e;
     kern<<<(unsigned)totalChains, split_block_threads(H), sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes);
@@ -682,7 +683,7 @@ cudaError_t launch_exact(const DrawParams& p, const SceneDev& sc, int lanes, cud
     const long long totalChains = (long long)p.numRows * p.numFrames;
     if (lanes <= 0)
     {
-        // measured on B200 (profiles/r02/exact_probe.md): one 720p frame (720 chains): split kernel with 2 shade warps 760 vs
+        // measured on B200 (profiles/r02/exact_probe_*.jsonl): one 720p frame (720 chains): split kernel with 2 shade warps 880 vs
         // 450 / 177 / 61 Mray/s for 32 / 8 / 1 lanes per chain; one 4K frame (2160 chains): 32 lanes 1.24 Gray/s (split 1.2);
         // 11 520 chains -> 32 lanes (2.63 vs 2.48 vs 1.2 Gray/s); 184 320 chains -> 1 lane, flat form (6.0 Gray/s)
         lanes = totalChains >= 100000 ? 1 : (totalChains >= 20000 ? 8 : (totalChains <= 1600 && p.spp <= kSplitMaxSpp ? 65 : 32));
@@ -698,6 +699,7 @@ cudaError_t launch_exact(const DrawParams& p, const SceneDev& sc, int lanes, cud
     case 9: e = launch_exact_flat_t<8>(p, sc, stream); break;        // flat form with 8 lanes per chain: measured 2x SLOWER than
                                                                      // the nested form at 11 520 chains (221 vs 111 ms), comparison only
     case 32: e = launch_exact_t<32>(p, sc, stream, block); break;
+    case 71: e = launch_exact_split_t<2, 0, 2>(p, sc, stream); break;   // comparison: shade warps calling shared out-of-line sqrt/div/libm
     case 70:                                                         // split kernel, roles on different SMs (2-CTA clusters)
         if (p.spp > kSplitMaxSpp || totalChains >= (1LL << 27)) return cudaErrorInvalidValue;
         e = launch_exact_cluster(p, sc, stream);
