@@ -24,6 +24,9 @@ def test_library_exports_every_declared_symbol(libs):
 
 def test_shim_exports_reference_api(libs):
     S = ctypes.CDLL(libs.SHIM_PATH)
+    hdr = open(os.path.join(ROOT, "include", "tpt_test_shim.h")).read()
+    for n in sorted(set(re.findall(r"\b(tpt_shim_[a-z0-9_]+)\s*\(", hdr))):
+        assert hasattr(S, n), f"{n} declared in include/tpt_test_shim.h but not exported by the shim"
     for sym in ("_Z14InitializeTestv", "_Z12ShutdownTestv", "_Z10UpdateTestfiiij", "_Z8DrawTestfiiiPfRij",
                 "_Z14GetObjectCountRiS_S_S_", "_Z12GetSceneDescPvS_S_S_Pi"):
         assert hasattr(S, sym), sym

@@ -7,7 +7,7 @@ import toypathtracer_b200 as tpt
 
 ctx = tpt.Context(0)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); sh = stream.cuda_stream
-cases = [(1280, 720, 1, (65, 72, 73, 69, 74))]
+cases = [(1280, 720, 1, (32, 64, 65, 66, 69, 70, 71)), (3840, 2160, 1, (32, 65)), (1280, 720, 16, (32, 8, 65)), (1280, 720, 256, (1,))]
 if len(sys.argv) > 1:
     cases = cases[: int(sys.argv[1])]
 for (w, h, nf, lanes_list) in cases:

@@ -10,7 +10,7 @@
 // Environment: TPT_MODE=exact|fast|refgpu|refgpu_fast (default exact: results bit-identical to the reference),
 // TPT_DEVICE=<n>, TPT_PIN_BACKBUFFER=1 (cudaHostRegister the caller's backbuffer once), TPT_BIG_SCENE=0|1,
 // TPT_MITSUBA=0|1.
-#include "../../include/tpt_b200.h"
+#include "../../include/tpt_b200.h"   // (include/tpt_test_shim.h documents this file's exports)
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>

@@ -44,7 +44,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity)
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DONE_S;\n"
         "WAIT_LOOP_S:\n"
-        "nanosleep.u32 128;\n"
+        "nanosleep.u32 128;\n"          // 32 .. 1024 ns measured: no difference in frame time
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@!p bra WAIT_LOOP_S;\n"
         "DONE_S:\n"

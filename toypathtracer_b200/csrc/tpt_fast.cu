@@ -15,7 +15,6 @@
 #include "tpt_device_utils.cuh"
 #include "tpt_launch.h"
 #include "tpt_fastdiv.h"
-#include "tpt_refgpu.cuh"
 
 namespace tpt {
 
@@ -1432,8 +1431,34 @@ k_fast_wave(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayou
     if (lane == 0 && rc) atomicAdd(p.rayCounter, (unsigned long long)rc);
 }
 
+} // namespace tpt
+#include "tpt_refgpu.cuh"
+namespace tpt {
+
+// The reference-GPU-compatible mode's native instance sweeps like the fast mode: expanded form on packed pairs (FFMA2).
+struct RgSetupK2
+{
+    using Hitter = FastHitterK2;
+    static constexpr int kMinBlocks = 6;
+    static size_t extra_smem(const SceneDev& sc) { return (((size_t)sc.stagedBytes + 127u) & ~(size_t)127u) - sc.stagedBytes + (size_t)((sc.count + 3) / 4 * 4) * 16; }
+    static __device__ __forceinline__ Hitter prepare(SceneView& sc, unsigned char* smem, const SceneBlobLayout& L, uint32_t stagedBytes)
+    {
+        float4* sphK = reinterpret_cast<float4*>(smem + L.offSph);
+        build_sphK(sc, sphK);                       // padded spheres get K = 1e30: never candidates (ComputeShader.hlsl:134)
+        __syncthreads();
+        float4* pairs = reinterpret_cast<float4*>(smem + ((stagedBytes + 127u) & ~127u));
+        build_sph_pairs(sc, sphK, pairs);
+        __syncthreads();
+        Hitter h; h.sphK = sc.sphShared; h.sphP = smem_u32(pairs); h.simdCount = sc.simdCount;
+        asm volatile("" : "+r"(h.sphK), "+r"(h.sphP));
+        return h;
+    }
+};
+
 cudaError_t launch_refgpu_fast(const DrawParams& p, const SceneDev& sc, int numSMs, cudaStream_t stream)
 {
+    const int simd = (sc.count + 3) / 4 * 4;
+    if (sc.kformOk && sc.kformMode == 2 && simd <= 1024) return launch_refgpu_t<false, RgSetupK2>(p, sc, numSMs, stream);
     return launch_refgpu_t<false>(p, sc, numSMs, stream);
 }
 

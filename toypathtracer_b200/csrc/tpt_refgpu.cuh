@@ -265,9 +265,28 @@ __device__ __forceinline__ bool rg_step(const DrawParams& p, const SceneView& sc
     return true;
 }
 
+// How the kernel sweeps: the plain setup uses the two-pass reference-form sweep (strict or native arithmetic); tpt_fast.cu
+// adds a setup with the expanded-form packed-pair sweep (FFMA2) for the native instance.
+template <bool EXACT> struct RgSetupPlain
+{
+    using Hitter = SerialHitter<EXACT, false>;
+    static constexpr int kMinBlocks = 1;
+    static size_t extra_smem(const SceneDev&) { return 0; }
+    static __device__ __forceinline__ Hitter prepare(SceneView& sc, unsigned char* smem, const SceneBlobLayout& L, uint32_t)
+    {
+        // the shader loops over sphereCount spheres only (ComputeShader.hlsl:134): the SIMD padding of the CPU path's SoA
+        // ("impossible" spheres, Maths.h:381-387) must never be a candidate here -> r^2 = -1e30 makes discr hugely negative
+        float4* sph = reinterpret_cast<float4*>(smem + L.offSph);
+        for (int i = sc.count + (int)threadIdx.x; i < sc.simdCount; i += blockDim.x) sph[i].w = -1.0e30f;
+        __syncthreads();
+        asm volatile("" : "+r"(sc.sphShared));      // the sweep's asm loads must not be hoisted above the rewrite
+        return Hitter();
+    }
+};
+
 // Persistent CTAs; every warp pulls slabs of kRgSlabPix pixels from a global counter and deals them to its idle lanes.
-template <bool EXACT>
-__global__ void __launch_bounds__(kRgThreads)
+template <bool EXACT, class Setup>
+__global__ void __launch_bounds__(kRgThreads, Setup::kMinBlocks)
 k_refgpu(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights, uint32_t stagedBytes,
          uint32_t numSlabs)
 {
@@ -275,13 +294,7 @@ k_refgpu(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L
     __shared__ uint64_t bar;
     stage_blob(smem, blob, stagedBytes, &bar);
     SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
-    // the shader loops over sphereCount spheres only (ComputeShader.hlsl:134): the SIMD padding of the CPU path's SoA
-    // ("impossible" spheres, Maths.h:381-387) must never be a candidate here -> r^2 = -1e30 makes discr hugely negative
-    float4* sph = reinterpret_cast<float4*>(smem + L.offSph);
-    for (int i = sc.count + (int)threadIdx.x; i < sc.simdCount; i += blockDim.x) sph[i].w = -1.0e30f;
-    __syncthreads();
-    asm volatile("" : "+r"(sc.sphShared));      // the sweep's asm loads must not be hoisted above the rewrite
-    SerialHitter<EXACT, false> hitter;
+    const typename Setup::Hitter hitter = Setup::prepare(sc, smem, L, stagedBytes);
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
     const uint32_t regionPix = (uint32_t)((long long)p.numRows * p.width);
@@ -329,14 +342,15 @@ k_refgpu(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L
     if (lane == 0 && rc) atomicAdd(p.rayCounter, (unsigned long long)rc);
 }
 
-template <bool EXACT>
+template <bool EXACT, class Setup = RgSetupPlain<EXACT>>
 static cudaError_t launch_refgpu_t(const DrawParams& p, const SceneDev& sc, int numSMs, cudaStream_t stream)
 {
-    auto kern = k_refgpu<EXACT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc.stagedBytes);
+    auto kern = k_refgpu<EXACT, Setup>;
+    const size_t dyn = sc.stagedBytes + Setup::extra_smem(sc);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
     int perSM = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kRgThreads, sc.stagedBytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kRgThreads, dyn);
     if (e != cudaSuccess) return e;
     if (perSM < 1) perSM = 1;
     const long long regionPix = (long long)p.numRows * p.width;
@@ -347,7 +361,7 @@ static cudaError_t launch_refgpu_t(const DrawParams& p, const SceneDev& sc, int 
     if (grid > ctasNeeded) grid = ctasNeeded;
     e = cudaMemsetAsync(p.workCounter, 0, sizeof(unsigned int), stream);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)grid, kRgThreads, sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes, (uint32_t)slabs);
+    kern<<<(unsigned)grid, kRgThreads, dyn, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes, (uint32_t)slabs);
     return cudaGetLastError();
 }
 
