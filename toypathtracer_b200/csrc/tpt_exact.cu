@@ -683,10 +683,10 @@ cudaError_t launch_exact(const DrawParams& p, const SceneDev& sc, int lanes, cud
     const long long totalChains = (long long)p.numRows * p.numFrames;
     if (lanes <= 0)
     {
-        // measured on B200 (profiles/r02/exact_probe_*.jsonl): one 720p frame (720 chains): split kernel with 2 shade warps 880 vs
-        // 450 / 177 / 61 Mray/s for 32 / 8 / 1 lanes per chain; one 4K frame (2160 chains): 32 lanes 1.24 Gray/s (split 1.2);
-        // 11 520 chains -> 32 lanes (2.63 vs 2.48 vs 1.2 Gray/s); 184 320 chains -> 1 lane, flat form (6.0 Gray/s)
-        lanes = totalChains >= 100000 ? 1 : (totalChains >= 20000 ? 8 : (totalChains <= 1600 && p.spp <= kSplitMaxSpp ? 65 : 32));
+        // measured on B200 (profiles/r02/exact_probe_final.jsonl): one 720p frame (720 chains): split kernel with 2 shade warps
+        // 885 vs 450 / 177 / 61 Mray/s for 32 / 8 / 1 lanes per chain; one 4K frame (2160 chains): split 1.38 vs 1.24 Gray/s;
+        // 11 520 chains: 32 lanes 2.63 vs 8 lanes 2.48 vs split 1.81 Gray/s; 184 320 chains -> 1 lane, flat form (5.8-6.0 Gray/s)
+        lanes = totalChains >= 100000 ? 1 : (totalChains >= 20000 ? 8 : (totalChains <= 2400 && p.spp <= kSplitMaxSpp ? 65 : 32));
     }
     cudaError_t e;
     const long long threads = totalChains * lanes;
