@@ -69,7 +69,7 @@ int tpt_set_spp(tpt_context* ctx, int spp);
  * write-out), "host_zero_copy" (default 1: with variant 8 a host-buffer draw whose `prev` has zero weight writes its finished
  * pixels directly into the caller's page-locked buffer over PCIe — no staging image, no device-to-host copy), "exact_lanes"
  * (0 auto; 64..67 = split kernel: one PATH warp per (frame,row) chain walks the RNG stream, 1..4 SHADE warps do the light
- * sampling / fold / blend off the critical path (auto for <= 1600 chains); 32 or 8 lanes per chain as nested loops; 1 = one
+ * sampling / fold / blend off the critical path (auto for <= 2400 chains); 32 or 8 lanes per chain as nested loops; 1 = one
  * thread per chain as a flat one-sweep-per-step state machine (auto for >= 100 000 chains); 2 = one thread per chain
  * nested, 9 = 8 lanes flat: measured slower, kept for comparison; 68/69 timing probes; 70 = the split kernel as 2-CTA
  * clusters with the roles on different SMs and the rings over DSMEM, 71 = shade warps calling out-of-line libm: both measured
