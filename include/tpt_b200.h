@@ -63,8 +63,8 @@ int tpt_set_camera(tpt_context* ctx, const void* camera88);
 
 /* DO_SAMPLES_PER_PIXEL (Config.h:22), default 4. */
 int tpt_set_spp(tpt_context* ctx, int spp);
-/* Implementation knobs (benchmarks/tests): "fast_variant" (-1 auto (default): 3 for device buffers, 8 for host-buffer draws that
- * can store straight into page-locked memory; 0 megakernel, 1/2 persistent tiles, 3/4 persistent slab queue with 128-bit L2
+/* Implementation knobs (benchmarks/tests): "fast_variant" (-1 auto (default): 3 for device buffers — 7 from 1024 spheres —, 8 for host-buffer
+ * draws that can store straight into page-locked memory; 0 megakernel, 1/2 persistent tiles, 3/4 persistent slab queue with 128-bit L2
  * reductions, 5 CTA-owned tiles, 6/7 block wavefront with material sort, 8 warp-owned pixel groups with coalesced 128-bit
  * write-out), "host_zero_copy" (default 1: with variant 8 a host-buffer draw whose `prev` has zero weight writes its finished
  * pixels directly into the caller's page-locked buffer over PCIe — no staging image, no device-to-host copy), "exact_lanes"

@@ -111,11 +111,15 @@ def test_c5_stress_4096_full_size(gpu_ctx, libs):
     pads = [(p[0], (p[1] - r0) // rs) for p in g["pads"] if (p[1] - r0) % rs == 0 and 0 <= (p[1] - r0) // rs < nr]
     assert not bits_differ(band, rows, pads).any()
     # fast mode on the same configuration: same estimator -> same rays per sample (8 spp x 2 M pixels: ~1e-3 noise)
-    fb = np.zeros((h, w, 4), np.float32)
-    frays = gpu_ctx.draw(0, 2, w, h, fb, flags=2, mode=1)
-    assert abs(frays / total - 1) < 4e-3
-    assert np.isfinite(fb).all()
-    assert rel_l2(fb, buf) < 1.3 * 0.194 * np.sqrt(2 / 8) * 2     # loose: other scene, other noise level; catches gross errors only
+    # (variant -1 = auto picks the material-sorted block wavefront for this sphere count; 3 = the slab queue)
+    for variant in (-1, 3):
+        gpu_ctx.set_option("fast_variant", variant)
+        fb = np.zeros((h, w, 4), np.float32)
+        frays = gpu_ctx.draw(0, 2, w, h, fb, flags=2, mode=1)
+        assert abs(frays / total - 1) < 4e-3, variant
+        assert np.isfinite(fb).all()
+        assert rel_l2(fb, buf) < 1.3 * 0.194 * np.sqrt(2 / 8) * 2, variant     # loose: other scene, other noise level; catches gross errors only
+    gpu_ctx.set_option("fast_variant", 3)
 
 
 # ---- fast mode against the bit-exact mode at scale ------------------------------------------------------------------

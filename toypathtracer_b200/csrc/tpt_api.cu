@@ -44,7 +44,7 @@ struct tpt_context
     int spp = 4;
 
     // options
-    int fastVariant = -1;     // -1 = auto: 3 (slab queue + L2 reductions) for device buffers, 8 (warp-owned groups, direct coalesced
+    int fastVariant = -1;     // -1 = auto: 3 (slab queue + L2 reductions; 7 = material-sorted block wavefront from 1024 spheres) for device buffers, 8 (warp-owned groups, direct coalesced
                               // write-out) when a host-buffer draw can store straight into page-locked memory
     int fastKForm = 2;        // 0: reference-form sweep, 1: expanded form, 2: expanded form with packed pairs (FFMA2); gated per scene by kformOk
     int fastAlphaZero = 0;
@@ -424,7 +424,9 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
         }
         else (void)cudaGetLastError();
     }
-    int fastVariant = ctx->fastVariant < 0 ? 3 : ctx->fastVariant;
+    // auto: the warp slab queue, except where the sweep dwarfs everything else (>= 1024 spheres): there the block wavefront
+    // that sorts its paths by material with ballot + prefix before Scatter() is faster (4096 spheres: 333 vs 312 Mray/s)
+    int fastVariant = ctx->fastVariant < 0 ? (ctx->scene.count >= 1024 ? 7 : 3) : ctx->fastVariant;
     if (!bufferOnDevice && mode == TPT_MODE_FAST && ctx->hostZeroCopy && (ctx->fastVariant < 0 || fast_variant_writes_final_pixels(ctx->fastVariant)))
     {
         // Host-buffer draw whose `prev` has zero weight, into page-locked memory the GPU can address: the trace kernel's
