@@ -426,7 +426,8 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
     }
     // auto: the warp slab queue, except where the sweep dwarfs everything else (>= 1024 spheres): there the block wavefront
     // that sorts its paths by material with ballot + prefix before Scatter() is faster (4096 spheres: 333 vs 312 Mray/s)
-    int fastVariant = ctx->fastVariant < 0 ? (ctx->scene.count >= 1024 ? 7 : 3) : ctx->fastVariant;
+    const bool waveFits = (long long)((numRows * (long long)width + 127) / 128) * 128 * ctx->spp * (numFrames < 256 ? numFrames : 256) <= 0x7fffffffLL;
+    int fastVariant = ctx->fastVariant < 0 ? (ctx->scene.count >= 1024 && waveFits ? 7 : 3) : ctx->fastVariant;
     if (!bufferOnDevice && mode == TPT_MODE_FAST && ctx->hostZeroCopy && (ctx->fastVariant < 0 || fast_variant_writes_final_pixels(ctx->fastVariant)))
     {
         // Host-buffer draw whose `prev` has zero weight, into page-locked memory the GPU can address: the trace kernel's
