@@ -151,6 +151,10 @@ int tpt_ipc_close(tpt_context* ctx, void* devPtr);
  * (toypathtracer_b200/csrc/tpt_libm.cuh) on n host floats. fn: 0 = sinf, 1 = cosf, 2 = powf(x, 5), 3 = powf(x, 1.0f/3.0f)
  * (the REFGPU mode's pow(x, 1.0/3.0), ComputeShader.hlsl:33). */
 int tpt_debug_libm(tpt_context* ctx, int fn, const float* in, float* out, long long n);
+/* Diagnostic used by the parity tests: nearest hit (HitWorld, Test.cpp:85-106) of n host rays {o.xyz, d.xyz} in the
+ * current scene with one sweep form of the fast kernels (kform 0 reference form, 1 expanded, 2 expanded on packed pairs,
+ * 3 conservative packed pass + reference-form decisions), tMin/tMax as Trace uses them. outId -1 = miss. */
+int tpt_debug_hit(tpt_context* ctx, int kform, const float* rays6, int* outId, float* outT, long long n);
 /* Diagnostic: device timestamps (ms since the start of the last progress-mode host draw) of the trace kernel's end,
  * each band copy's end and the draw's end. Returns minus the number of entries written. */
 int tpt_debug_timeline(tpt_context* ctx, float* outMs, int capacity);

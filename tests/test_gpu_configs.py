@@ -120,6 +120,19 @@ def test_c5_stress_4096_full_size(gpu_ctx, libs):
         assert np.isfinite(fb).all()
         assert rel_l2(fb, buf) < 1.3 * 0.194 * np.sqrt(2 / 8) * 2, variant     # loose: other scene, other noise level; catches gross errors only
     gpu_ctx.set_option("fast_variant", 3)
+    # This scene fails the expanded-form accuracy gate (centres up to |s| ~ 45), so the queue kernel runs the CONSERVATIVE
+    # packed pass 1 + reference-form pass 2 (FastHitterK2C, one 768-thread CTA per SM). Its hit decisions are the
+    # reference-form sweep's ray by ray (test_gpu_fast.py::test_sweep_forms_ray_by_ray); the two KERNELS agree up to the
+    # differently contracted (-fmad) shading code of each template instance: 6..140 rays of 129.6 M, and exactly 0 when the
+    # translation unit is built without implicit contraction (profiles/r02/determinism_fast_nofmad.log).
+    out = []
+    for kform in (2, 0):
+        gpu_ctx.set_option("fast_kform", kform)
+        fb = np.zeros((h, w, 4), np.float32)
+        out.append((gpu_ctx.draw(0, 2, w, h, fb, flags=2, mode=1), fb))
+    gpu_ctx.set_option("fast_kform", 2)
+    assert abs(out[0][0] / out[1][0] - 1) < 5e-6, (out[0][0], out[1][0])
+    assert rel_l2(out[0][1], out[1][1]) < 1e-3
 
 
 # ---- fast mode against the bit-exact mode at scale ------------------------------------------------------------------

@@ -73,6 +73,7 @@ def _load_lib():
     L.tpt_tonemap_srgb8.argtypes = [vp, vp, ci, ci, ci, vp, ci, vp]; L.tpt_tonemap_srgb8.restype = ci
     L.tpt_tonemap_rgba8.argtypes = [vp, vp, ci, ci, ci, vp, ci, ci, ci, ci, vp]; L.tpt_tonemap_rgba8.restype = ci
     L.tpt_debug_libm.argtypes = [vp, ci, vp, vp, cll]; L.tpt_debug_libm.restype = ci
+    L.tpt_debug_hit.argtypes = [vp, ci, vp, vp, vp, cll]; L.tpt_debug_hit.restype = ci
     cull = ctypes.c_ulonglong
     L.tpt_mem_alloc.argtypes = [vp, cull, ctypes.POINTER(vp)]; L.tpt_mem_alloc.restype = ci
     L.tpt_mem_free.argtypes = [vp, vp]; L.tpt_mem_free.restype = ci
@@ -234,6 +235,14 @@ class Context:
         out = np.empty_like(x)
         self._check(self._L.tpt_debug_libm(self._h, fn, x.ctypes.data, out.ctypes.data, x.size), "tpt_debug_libm")
         return out
+
+    def debug_hit(self, kform: int, rays: np.ndarray):
+        """Nearest hit of rays[n, 6] = {o.xyz, d.xyz} with sweep form `kform` of the fast kernels -> (ids int32, t float32)."""
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        ids = np.empty(len(rays), np.int32)
+        t = np.empty(len(rays), np.float32)
+        self._check(self._L.tpt_debug_hit(self._h, kform, rays.ctypes.data, ids.ctypes.data, t.ctypes.data, len(rays)), "tpt_debug_hit")
+        return ids, t
 
     def tonemap_srgb8(self, image, width: int, height: int) -> np.ndarray:
         addr, on_dev, _keep = _as_ptr(image)

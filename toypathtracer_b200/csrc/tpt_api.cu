@@ -424,10 +424,13 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
         }
         else (void)cudaGetLastError();
     }
-    // auto: the warp slab queue, except where the sweep dwarfs everything else (>= 1024 spheres): there the block wavefront
-    // that sorts its paths by material with ballot + prefix before Scatter() is faster (4096 spheres: 333 vs 312 Mray/s)
+    // auto: the warp slab queue. Only where the sweep dwarfs everything else (>= 1024 spheres) AND the queue kernel cannot
+    // run a packed-pair sweep (pair array does not fit, or "fast_kform" < 2) is the block wavefront that sorts its paths
+    // by material before Scatter() faster (4096 spheres, Mray/s: queue packed 443, wavefront 333, queue scalar 312)
     const bool waveFits = (long long)((numRows * (long long)width + 127) / 128) * 128 * ctx->spp * (numFrames < 256 ? numFrames : 256) <= 0x7fffffffLL;
-    int fastVariant = ctx->fastVariant < 0 ? (ctx->scene.count >= 1024 && waveFits ? 7 : 3) : ctx->fastVariant;
+    SceneDev autoScene = ctx->scene;
+    autoScene.kformMode = ctx->fastKForm;
+    int fastVariant = ctx->fastVariant < 0 ? (ctx->scene.count >= 1024 && waveFits && fast_queue_kform(autoScene) < 2 ? 7 : 3) : ctx->fastVariant;
     if (!bufferOnDevice && mode == TPT_MODE_FAST && ctx->hostZeroCopy && (ctx->fastVariant < 0 || fast_variant_writes_final_pixels(ctx->fastVariant)))
     {
         // Host-buffer draw whose `prev` has zero weight, into page-locked memory the GPU can address: the trace kernel's
@@ -826,6 +829,27 @@ int tpt_debug_libm(tpt_context* ctx, int fn, const float* in, float* out, long l
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(dIn); cudaFree(dOut);
     if (e != cudaSuccess) return fail(ctx, e, "tpt_debug_libm");
+    return 0;
+}
+
+int tpt_debug_hit(tpt_context* ctx, int kform, const float* rays, int* outId, float* outT, long long n)
+{
+    if (!ctx || !rays || !outId || !outT || n <= 0 || kform < 0 || kform > 3) return (int)cudaErrorInvalidValue;
+    if (!ctx->scene.blob) return fail_msg(ctx, "tpt_debug_hit: no scene");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    float *dRays = nullptr, *dT = nullptr;
+    int* dId = nullptr;
+    cudaError_t e = cudaMalloc(&dRays, (size_t)n * 24);
+    if (e == cudaSuccess) e = cudaMalloc(&dT, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&dId, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->uploadDone[ctx->curBlob], 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dRays, rays, (size_t)n * 24, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = launch_debug_hit(ctx->scene, kform, dRays, dId, dT, n, ctx->numSMs, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(outId, dId, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(outT, dT, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dRays); cudaFree(dT); cudaFree(dId);
+    if (e != cudaSuccess) return fail(ctx, e, "tpt_debug_hit");
     return 0;
 }
 

@@ -570,6 +570,96 @@ struct FastHitterK2
     }
 };
 
+// Conservative form for scenes the expanded form is NOT accurate enough for (centres far from the origin: the gate in
+// tpt_set_scene fails, e.g. the 4096-sphere stress scene): pass 1 is the packed expanded-form sweep with an error bound
+// folded into its additive constants, so it can only ADD candidates; pass 2 evaluates every candidate in the reference
+// form (Maths.cpp:97-102) on the untouched {s, r^2} array, so hit decisions and distances are the reference form's
+// (tpt_debug_hit: bit-identical ids and distances on millions of rays). Bound (u = 2^-24, |d| = 1): |d nb| <= 6u(|s|+|o|),
+// |d c| <= 9u(|s|+|o|)^2, hence |d discr| <= 22u(|s|+|o|)^2 for the expanded form and <= 12u(|s|+|o|)^2 for the reference
+// form; with (|s|+|o|)^2 <= 2(|s|^2 + o.o) the margin eps_i = 2^-17 (|s_i|^2 + o.o) = 64u * 2(...) covers both. It splits
+// into a per-sphere constant (stored with -K_i) and a per-ray constant (folded into -o.o): no extra instruction, and a
+// far-away sphere (the ground, |s| = 1000) does not loosen the test of the others. The "wholly behind" rejection needs no
+// margin of its own: a sphere it drops wrongly has a true nb below 6u(|s|+|o|) << tMin/2, i.e. both roots below tMin.
+struct FastHitterK2C
+{
+    uint32_t sph;       // shared-memory address of the ORIGINAL {sx, sy, sz, r^2}[simdCount]   (pass 2)
+    uint32_t sphP;      // pair array {x0,x1,y0,y1}{z0,z1,-K0,-K1}                             (pass 1)
+    int simdCount;
+    __device__ __forceinline__ int hit(const SceneView&, V3 o, V3 d, float tMin, float tMax, float& tOut) const
+    {
+        const float nod = -fmaf(o.x, d.x, fmaf(o.y, d.y, o.z * d.z));
+        const float oo = fmaf(o.x, o.x, fmaf(o.y, o.y, o.z * o.z));
+        const unsigned long long DX = f2_bcast(d.x), DY = f2_bcast(d.y), DZ = f2_bcast(d.z), NOD = f2_bcast(nod);
+        const unsigned long long BX = f2_bcast(2.0f * o.x), BY = f2_bcast(2.0f * o.y), BZ = f2_bcast(2.0f * o.z);
+        const unsigned long long NOO = f2_bcast(oo * 7.62939453125e-6f - oo);     // the ray's share of the margin: 2^-17 o.o
+        float bestT = tMax;
+        int bestId = -1;
+        for (int base = 0; base < simdCount; base += 32)
+        {
+            const int n = simdCount - base < 32 ? simdCount - base : 32;
+            uint32_t neg = 0;
+#pragma unroll
+            for (int k = 0; k < 32; k += 4)
+            {
+                if (k < n)
+                {
+#pragma unroll
+                    for (int j = 0; j < 4; j += 2)
+                    {
+                        unsigned long long xx, yy, zz, kk;
+                        const uint32_t a = sphP + (uint32_t)((base + k + j) >> 1) * 32u;
+                        asm("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(xx), "=l"(yy) : "r"(a));
+                        asm("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(zz), "=l"(kk) : "r"(a + 16u));
+                        const unsigned long long nb = f2_fma(xx, DX, f2_fma(yy, DY, f2_fma(zz, DZ, NOD)));
+                        const unsigned long long negc = f2_fma(xx, BX, f2_fma(yy, BY, f2_fma(zz, BZ, f2_add(kk, NOO))));
+                        const unsigned long long discr = f2_fma(nb, nb, negc);
+                        const uint32_t r0 = (uint32_t)discr | ((uint32_t)nb & (uint32_t)negc);
+                        const uint32_t r1 = (uint32_t)(discr >> 32) | ((uint32_t)(nb >> 32) & (uint32_t)(negc >> 32));
+                        neg = __funnelshift_l(r0, neg, 1);
+                        neg = __funnelshift_l(r1, neg, 1);
+                    }
+                }
+            }
+            uint32_t cand = ~neg & (n == 32 ? 0xffffffffu : ((1u << n) - 1u));
+            while (cand)
+            {
+                const int bit = 31 - __clz((int)cand);
+                cand &= ~(1u << bit);
+                const int i = base + (n - 1 - bit);
+                Q4 s;
+                asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(s.x), "=f"(s.y), "=f"(s.z), "=f"(s.w) : "r"(sph + (uint32_t)i * 16u));
+                float nb;
+                const float discr = sphere_discr<false>(s, o, d, nb);         // reference form
+                if (discr > 0.0f)
+                {
+                    const float sq = M<false>::sqrt_(discr);
+                    float t = nb - sq;
+                    if (t <= tMin) t = nb + sq;
+                    if (t > tMin && t < bestT) { bestT = t; bestId = i; }
+                }
+            }
+        }
+        tOut = bestT;
+        return bestId;
+    }
+};
+
+// Pair array for FastHitterK2C straight from the staged {s, r^2} array (which stays as it is): -K_i plus the sphere's share
+// of the margin, 2^-17 |s_i|^2, in double precision; padded "impossible" spheres get -1e30 (never candidates).
+__device__ __forceinline__ void build_sph_pairs_from_r2(const SceneView& sc, const float4* sph, float4* pairs)
+{
+    for (int p = threadIdx.x; 2 * p < sc.simdCount; p += blockDim.x)
+    {
+        const float4 a = sph[2 * p], b = sph[2 * p + 1];
+        const double Sa = (double)a.x * a.x + (double)a.y * a.y + (double)a.z * a.z, Sb = (double)b.x * b.x + (double)b.y * b.y + (double)b.z * b.z;
+        const double m = 7.62939453125e-6;      // 2^-17
+        // round the constant UP (towards the permissive side): the margin must not shrink by the rounding of -K
+        const float na = __double2float_ru(Sa * m - (Sa - (double)a.w)), nbv = __double2float_ru(Sb * m - (Sb - (double)b.w));
+        pairs[2 * p] = make_float4(a.x, b.x, a.y, b.y);
+        pairs[2 * p + 1] = make_float4(a.z, b.z, 2 * p < sc.count ? na : -1.0e30f, 2 * p + 1 < sc.count ? nbv : -1.0e30f);
+    }
+}
+
 // Pair array for FastHitterK2 from the {s, K} array build_sphK() left in place: pair p = spheres 2p, 2p+1 as
 // {x0, x1, y0, y1} {z0, z1, -K0, -K1}.
 __device__ __forceinline__ void build_sph_pairs(const SceneView& sc, const float4* sphK, float4* pairs)
@@ -705,30 +795,37 @@ __device__ __forceinline__ bool path_step(const SceneView& sc, QPath& st, unsign
     return finished;
 }
 
-template <int MINB, int KFORM>     // KFORM 0: reference-form sweep, 1: expanded form, 2: expanded form, packed pairs (FFMA2)
-__global__ void __launch_bounds__(kQueueThreads, MINB)
+// KFORM 0: reference-form sweep, 1: expanded form, 2: expanded form on packed pairs (FFMA2), 3: packed-pair pass 1 made
+// conservative + reference-form pass 2 (FastHitterK2C: any scene). THREADS: 128 (6 CTAs/SM) for scenes whose staged
+// geometry is small; one big CTA per SM when the sphere arrays fill most of an SM's shared memory.
+// Dynamic shared memory: [staged blob][pair array (KFORM 2/3)][per-warp camera-ray buffers, 2 KB per warp at raysOffset].
+template <int THREADS, int MINB, int KFORM>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights,
-             uint32_t stagedBytes, uint32_t numSlabs, uint32_t S, unsigned int* __restrict__ bandDone, uint32_t mtilesPerBand)
+             uint32_t stagedBytes, uint32_t numSlabs, uint32_t S, unsigned int* __restrict__ bandDone, uint32_t mtilesPerBand,
+             uint32_t raysOffset)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     __shared__ float sW[kMaxFramesPerDraw];
     // camera rays of the warp's current slab, generated 4 per lane in one convergent burst when the slab is fetched:
     // {origin.xyz, rng state} {direction.xyz, pixel offset}; regeneration then only pops an entry.
-    __shared__ float4 sRays[kQueueThreads / 32][kSlabPix][2];
+    float4 (*sRays)[kSlabPix][2] = reinterpret_cast<float4 (*)[kSlabPix][2]>(smem + raysOffset);
     stage_blob(smem, blob, stagedBytes, &bar);
     if (threadIdx.x == 0) { float wp; blend_weights(p, sW, wp); }
     SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
     float4* sphK = reinterpret_cast<float4*>(smem + L.offSph);
-    if (KFORM) build_sphK(sc, sphK);
+    if (KFORM == 1 || KFORM == 2) build_sphK(sc, sphK);
     __syncthreads();
-    float4* pairs = reinterpret_cast<float4*>(smem + ((stagedBytes + 127u) & ~127u));     // KFORM 2: behind the staged blob
+    float4* pairs = reinterpret_cast<float4*>(smem + ((stagedBytes + 127u) & ~127u));     // KFORM 2/3: behind the staged blob
     if (KFORM == 2) { build_sph_pairs(sc, sphK, pairs); __syncthreads(); }
+    if (KFORM == 3) { build_sph_pairs_from_r2(sc, sphK, pairs); __syncthreads(); }
     FastHitterK hitK; hitK.sphK = sc.sphShared; hitK.simdCount = sc.simdCount;
     FastHitterK2 hitK2; hitK2.sphK = sc.sphShared; hitK2.sphP = smem_u32(pairs); hitK2.simdCount = sc.simdCount;
+    FastHitterK2C hitK2C; hitK2C.sph = sc.sphShared; hitK2C.sphP = smem_u32(pairs); hitK2C.simdCount = sc.simdCount;
     // the sweep's loads are plain (schedulable) asm: make their address opaque AFTER the barrier so that none of them can
-    // be hoisted above the in-place {s, r^2} -> {s, K} rewrite
-    asm volatile("" : "+r"(hitK.sphK), "+r"(hitK2.sphK), "+r"(hitK2.sphP));
+    // be hoisted above the in-place {s, r^2} -> {s, K} rewrite / the construction of the pair array
+    asm volatile("" : "+r"(hitK.sphK), "+r"(hitK2.sphK), "+r"(hitK2.sphP), "+r"(hitK2C.sph), "+r"(hitK2C.sphP));
     SerialHitter<false> hitS;
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
@@ -808,7 +905,7 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
         }
         if (!__any_sync(0xffffffffu, st.active)) break;
 
-        const bool finished = KFORM == 2 ? path_step(sc, st, rc, hitK2) : (KFORM == 1 ? path_step(sc, st, rc, hitK) : path_step(sc, st, rc, hitS));
+        const bool finished = KFORM == 3 ? path_step(sc, st, rc, hitK2C) : KFORM == 2 ? path_step(sc, st, rc, hitK2) : (KFORM == 1 ? path_step(sc, st, rc, hitK) : path_step(sc, st, rc, hitS));
         if (finished)
         {
             red_add_f4(p.image + (size_t)st.pixOff * 4, st.col.x * st.weight, st.col.y * st.weight, st.col.z * st.weight);
@@ -1462,6 +1559,113 @@ cudaError_t launch_refgpu_fast(const DrawParams& p, const SceneDev& sc, int numS
     return launch_refgpu_t<false>(p, sc, numSMs, stream);
 }
 
+template <int THREADS, int MINB, int KFORM>
+static cudaError_t launch_queue_t(const DrawParams& p, const SceneDev& sc, int numSMs, cudaStream_t stream,
+                                  unsigned int* bandDone, int numBands, unsigned int* bandExpected)
+{
+    auto kern = k_fast_queue<THREADS, MINB, KFORM>;
+    const int simd = (sc.count + 3) / 4 * 4;
+    const size_t stagedAl = ((size_t)sc.stagedBytes + 127u) & ~(size_t)127u;
+    const size_t raysOffset = stagedAl + (KFORM >= 2 ? (((size_t)simd * 16 + 127u) & ~(size_t)127u) : 0);
+    const size_t dyn3 = raysOffset + (size_t)(THREADS / 32) * kSlabPix * 32;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn3);
+    if (e != cudaSuccess) return e;
+    int perSM = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, THREADS, dyn3);
+    if (e != cudaSuccess) return e;
+    if (perSM < 1) perSM = 1;
+    float wPrev = 1.0f;
+    for (int f = 0; f < p.numFrames; ++f) wPrev *= lerp_fac(p.frame0 + f, p.flags);
+    const long long regionPix = (long long)p.numRows * p.width;
+    k_prepare_image<<<(unsigned)((regionPix + 255) / 256), 256, 0, stream>>>(p, wPrev);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const uint32_t S = (uint32_t)(p.spp * p.numFrames);
+    const long long slabs = ((regionPix + kSlabPix - 1) / kSlabPix) * S;
+    if (slabs > 0x7fffffffLL) return cudaErrorInvalidValue;
+    long long grid = (long long)numSMs * perSM;
+    const long long ctasNeeded = (slabs + THREADS / 32 - 1) / (THREADS / 32);
+    if (grid > ctasNeeded) grid = ctasNeeded;
+    e = cudaMemsetAsync(p.workCounter, 0, sizeof(unsigned int), stream);
+    if (e != cudaSuccess) return e;
+    // optional progress bands (host-buffer draws): band b = macro-tiles [b*mpb, (b+1)*mpb)
+    const uint32_t mtiles = (uint32_t)((regionPix + kSlabPix - 1) / kSlabPix);
+    uint32_t mpb = 0;
+    if (bandDone && numBands > 0)
+    {
+        mpb = (mtiles + (uint32_t)numBands - 1) / (uint32_t)numBands;
+        for (int b = 0; b < numBands; ++b)
+        {
+            const long long p0 = (long long)b * mpb * kSlabPix, p1 = (long long)(b + 1) * mpb * kSlabPix;
+            const long long px = (p1 < regionPix ? p1 : regionPix) - (p0 < regionPix ? p0 : regionPix);
+            bandExpected[b] = (unsigned int)(px * S);
+        }
+    }
+    kern<<<(unsigned)grid, THREADS, dyn3, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes,
+                                                      (uint32_t)slabs, S, mpb ? bandDone : nullptr, mpb ? mpb : 1u, (uint32_t)raysOffset);
+    return cudaGetLastError();
+}
+
+// Diagnostic (tpt_debug_hit): the nearest-hit query of one sweep form on caller-supplied rays, staged exactly like
+// k_fast_queue stages it. The parity tests compare forms ray by ray with it (ids and distance bits).
+template <int KFORM>
+__global__ void __launch_bounds__(256)
+k_debug_hit(const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights, uint32_t stagedBytes,
+            const float* __restrict__ rays, int* __restrict__ outId, float* __restrict__ outT, long long n)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    stage_blob(smem, blob, stagedBytes, &bar);
+    SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
+    float4* sphK = reinterpret_cast<float4*>(smem + L.offSph);
+    if (KFORM == 1 || KFORM == 2) build_sphK(sc, sphK);
+    __syncthreads();
+    float4* pairs = reinterpret_cast<float4*>(smem + ((stagedBytes + 127u) & ~127u));
+    if (KFORM == 2) { build_sph_pairs(sc, sphK, pairs); __syncthreads(); }
+    if (KFORM == 3) { build_sph_pairs_from_r2(sc, sphK, pairs); __syncthreads(); }
+    FastHitterK hitK; hitK.sphK = sc.sphShared; hitK.simdCount = sc.simdCount;
+    FastHitterK2 hitK2; hitK2.sphK = sc.sphShared; hitK2.sphP = smem_u32(pairs); hitK2.simdCount = sc.simdCount;
+    FastHitterK2C hitK2C; hitK2C.sph = sc.sphShared; hitK2C.sphP = smem_u32(pairs); hitK2C.simdCount = sc.simdCount;
+    asm volatile("" : "+r"(hitK.sphK), "+r"(hitK2.sphK), "+r"(hitK2.sphP), "+r"(hitK2C.sph), "+r"(hitK2C.sphP));
+    SerialHitter<false> hitS;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    {
+        const V3 o{rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]}, d{rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]};
+        float t = TPT_MAX_T;
+        int id;
+        if (KFORM == 3) id = hitK2C.hit(sc, o, d, TPT_MIN_T, TPT_MAX_T, t);
+        else if (KFORM == 2) id = hitK2.hit(sc, o, d, TPT_MIN_T, TPT_MAX_T, t);
+        else if (KFORM == 1) id = hitK.hit(sc, o, d, TPT_MIN_T, TPT_MAX_T, t);
+        else id = hitS.hit(sc, o, d, TPT_MIN_T, TPT_MAX_T, t);
+        outId[i] = id;
+        outT[i] = t;
+    }
+}
+
+cudaError_t launch_debug_hit(const SceneDev& sc, int kform, const float* dRays, int* dId, float* dT, long long n, int numSMs, cudaStream_t stream)
+{
+    auto kern = kform == 3 ? k_debug_hit<3> : kform == 2 ? k_debug_hit<2> : kform == 1 ? k_debug_hit<1> : k_debug_hit<0>;
+    const int simd = (sc.count + 3) / 4 * 4;
+    const size_t stagedAl = ((size_t)sc.stagedBytes + 127u) & ~(size_t)127u;
+    const size_t dyn = stagedAl + (kform >= 2 ? (size_t)simd * 16 : 0);
+    if (dyn > 200 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    kern<<<numSMs, 256, dyn, stream>>>(sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes, dRays, dId, dT, n);
+    return cudaGetLastError();
+}
+
+// Sweep form the slab-queue kernel (variants 3/4) runs for this scene and option set: see k_fast_queue.
+int fast_queue_kform(const SceneDev& sc)
+{
+    const int simd = (sc.count + 3) / 4 * 4;
+    const size_t pairBytes = (size_t)simd * 16, stagedAl = ((size_t)sc.stagedBytes + 127u) & ~(size_t)127u;
+    const bool pairsFit = stagedAl + pairBytes + 24 * 2048 <= 200 * 1024;
+    if (sc.kformMode == 0) return 0;
+    if (sc.kformOk) return (sc.kformMode == 1 || !pairsFit) ? 1 : 2;
+    return (sc.kformMode == 2 && pairsFit) ? 3 : 0;
+}
+
 int fast_slab_pixels() { return kSlabPix; }
 
 int fast_kernel_launches(const DrawParams&, int variant) { return (variant == 3 || variant == 4 || variant == 6 || variant == 7) ? 2 : 1; }
@@ -1502,50 +1706,20 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
     }
     if (variant == 3 || variant == 4)
     {
-        // expanded-form sweep (8 FP32 slots/test): K replaces r^2 in the staged sphere array
-        // sweep form: 2 = expanded + packed pairs (FFMA2; the pair array costs 16 B per sphere of extra shared memory),
-        // 1 = expanded, 0 = reference form
+        // sweep form: 2 = expanded + packed pairs (FFMA2; the pair array costs 16 B per sphere of extra shared memory) where
+        // the scene passes the accuracy gate, 3 = the conservative packed form + reference-form pass 2 where it does not,
+        // 1 / 0 = scalar expanded / reference form (comparison, or scenes too large for the pair array)
         const int simd = (sc.count + 3) / 4 * 4;
-        const int kform = !sc.kformOk ? 0 : (sc.kformMode == 1 || simd > 1024 ? 1 : 2);
-        auto kern = variant == 3 ? (kform == 2 ? k_fast_queue<TPT_QUEUE_MINB, 2> : kform == 1 ? k_fast_queue<TPT_QUEUE_MINB, 1> : k_fast_queue<TPT_QUEUE_MINB, 0>)
-                                 : (kform == 2 ? k_fast_queue<7, 2> : kform == 1 ? k_fast_queue<7, 1> : k_fast_queue<7, 0>);
-        const size_t dyn3 = kform == 2 ? ((sc.stagedBytes + 127u) & ~127u) + (size_t)simd * 16 : sc.stagedBytes;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn3);
-        if (e != cudaSuccess) return e;
-        int perSM = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kQueueThreads, dyn3);
-        if (e != cudaSuccess) return e;
-        if (perSM < 1) perSM = 1;
-        float wPrev = 1.0f;
-        for (int f = 0; f < p.numFrames; ++f) wPrev *= lerp_fac(p.frame0 + f, p.flags);
-        const long long regionPix = (long long)p.numRows * p.width;
-        k_prepare_image<<<(unsigned)((regionPix + 255) / 256), 256, 0, stream>>>(p, wPrev);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        const uint32_t S = (uint32_t)(p.spp * p.numFrames);
-        const long long slabs = ((regionPix + kSlabPix - 1) / kSlabPix) * S;
-        if (slabs > 0x7fffffffLL) return cudaErrorInvalidValue;
-        long long grid = (long long)numSMs * perSM;
-        const long long warpsNeeded = (slabs + kQueueThreads / 32 - 1) / (kQueueThreads / 32);
-        if (grid > warpsNeeded) grid = warpsNeeded;
-        e = cudaMemsetAsync(p.workCounter, 0, sizeof(unsigned int), stream);
-        if (e != cudaSuccess) return e;
-        // optional progress bands (host-buffer draws): band b = macro-tiles [b*mpb, (b+1)*mpb)
-        const uint32_t mtiles = (uint32_t)((regionPix + kSlabPix - 1) / kSlabPix);
-        uint32_t mpb = 0;
-        if (bandDone && numBands > 0)
-        {
-            mpb = (mtiles + (uint32_t)numBands - 1) / (uint32_t)numBands;
-            for (int b = 0; b < numBands; ++b)
-            {
-                const long long p0 = (long long)b * mpb * kSlabPix, p1 = (long long)(b + 1) * mpb * kSlabPix;
-                const long long px = (p1 < regionPix ? p1 : regionPix) - (p0 < regionPix ? p0 : regionPix);
-                bandExpected[b] = (unsigned int)(px * S);
-            }
-        }
-        kern<<<(unsigned)grid, kQueueThreads, dyn3, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes,
-                                                                (uint32_t)slabs, S, mpb ? bandDone : nullptr, mpb ? mpb : 1u);
-        return cudaGetLastError();
+        const size_t pairBytes = (size_t)simd * 16, stagedAl = ((size_t)sc.stagedBytes + 127u) & ~(size_t)127u;
+        const int kform = fast_queue_kform(sc);
+        // small scenes: 128-thread CTAs, 6 (variant 4: 7) per SM; scenes whose arrays fill most of an SM's shared memory: ONE
+        // 768-thread CTA per SM (24 warps share one copy of the geometry instead of 2 CTAs x 4 warps with a copy each)
+        const bool big = stagedAl + ((kform >= 2) ? pairBytes : 0) + 4 * 2048 > 36 * 1024;
+#define TPT_LAUNCH_QUEUE(T, M, K) return launch_queue_t<T, M, K>(p, sc, numSMs, stream, bandDone, numBands, bandExpected)
+        if (big) { switch (kform) { case 3: TPT_LAUNCH_QUEUE(768, 1, 3); case 2: TPT_LAUNCH_QUEUE(768, 1, 2); case 1: TPT_LAUNCH_QUEUE(768, 1, 1); default: TPT_LAUNCH_QUEUE(768, 1, 0); } }
+        if (variant == 3) { switch (kform) { case 3: TPT_LAUNCH_QUEUE(128, TPT_QUEUE_MINB, 3); case 2: TPT_LAUNCH_QUEUE(128, TPT_QUEUE_MINB, 2); case 1: TPT_LAUNCH_QUEUE(128, TPT_QUEUE_MINB, 1); default: TPT_LAUNCH_QUEUE(128, TPT_QUEUE_MINB, 0); } }
+        switch (kform) { case 3: TPT_LAUNCH_QUEUE(128, 7, 3); case 2: TPT_LAUNCH_QUEUE(128, 7, 2); case 1: TPT_LAUNCH_QUEUE(128, 7, 1); default: TPT_LAUNCH_QUEUE(128, 7, 0); }   // variant 4: 72 registers, 21.05 vs 21.14 Gray/s
+#undef TPT_LAUNCH_QUEUE
     }
     if (variant == 8)
     {

@@ -22,6 +22,10 @@ cudaError_t launch_exact(const DrawParams& p, const SceneDev& sc, int lanes, cud
 // the reference's progressive blend (Test.cpp:272-276,293-295) of p.numFrames frames of per-frame colours in p.scratch
 cudaError_t launch_resolve_exact(const DrawParams& p, cudaStream_t stream);
 cudaError_t launch_debug_libm(int fn, const float* dIn, float* dOut, long long n, cudaStream_t stream);
+// sweep form variants 3/4 run for this scene (0 reference, 1 expanded, 2 packed pairs, 3 conservative packed)
+int fast_queue_kform(const SceneDev& sc);
+// nearest hit of n rays {o.xyz, d.xyz} with one sweep form of the fast kernels (0 reference, 1 expanded, 2 packed pairs, 3 conservative)
+cudaError_t launch_debug_hit(const SceneDev& sc, int kform, const float* dRays, int* dId, float* dT, long long n, int numSMs, cudaStream_t stream);
 // variant: see tpt_fast.cu
 // bandDone (optional, variant 3/4 only): device counters [numBands]; the kernel publishes finished paths per band of
 // macro-tiles, bandExpected[b] receives the final count of band b (host array) and kSlabPix*ceil(mtiles/numBands) pixels
