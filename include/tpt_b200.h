@@ -63,7 +63,7 @@ int tpt_set_camera(tpt_context* ctx, const void* camera88);
 
 /* DO_SAMPLES_PER_PIXEL (Config.h:22), default 4. */
 int tpt_set_spp(tpt_context* ctx, int spp);
-/* Implementation knobs (benchmarks/tests): "fast_variant" (-1 auto (default): 3 for device buffers — 7 from 1024 spheres —, 8 for host-buffer
+/* Implementation knobs (benchmarks/tests): "fast_variant" (-1 auto (default): 3 for device buffers (7 from 1024 spheres when the packed pair array does not fit in shared memory), 8 for host-buffer
  * draws that can store straight into page-locked memory; 0 megakernel, 1/2 persistent tiles, 3/4 persistent slab queue with 128-bit L2
  * reductions, 5 CTA-owned tiles, 6/7 block wavefront with material sort, 8 warp-owned pixel groups with coalesced 128-bit
  * write-out), "host_zero_copy" (default 1: with variant 8 a host-buffer draw whose `prev` has zero weight writes its finished
@@ -81,7 +81,8 @@ int tpt_set_spp(tpt_context* ctx, int spp);
  * copy stream waits on them with cuStreamWaitValue32, "progress_bands" bands, default 4; 0 falls back to host_bands),
  * "fast_kform" (fast kernels' sphere sweep: 0 reference form, 1 expanded form, 2 (default) expanded form evaluated two
  * spheres per instruction with Blackwell's packed fma.rn.f32x2; 1 and 2 only when the scene passes the gate in
- * tpt_set_scene; per context), "fast_alpha_zero" (default 0; 1: fast-mode draws whose `prev` has zero weight write
+ * tpt_set_scene — a scene that fails it gets, with 2, the packed sweep made conservative by a folded-in error bound
+ * plus reference-form hit decisions, and the reference form otherwise; per context), "fast_alpha_zero" (default 0; 1: fast-mode draws whose `prev` has zero weight write
  * alpha = 0 instead of keeping the buffer's alpha — saves the read over NVLink when the buffer is a peer GPU's),
  * "exact_lookahead" (default 0; L > 1: an exact-mode draw of ONE frame that misses the cache traces frames [f, f+L) in a
  * single launch and keeps their per-frame colours; the calls for the following frames only blend their cached frame into

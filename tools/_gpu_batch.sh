@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-timeout -k 5 900 python -m pytest tests/test_gpu_configs.py tests/test_gpu_fast.py -m gpu -x -q -rf > gpurun_out/pytest14.log 2>&1; tail -8 gpurun_out/pytest14.log
-timeout -k 5 600 ncu --set full --clock-control none --import-source on -k regex:k_fast_queue -c 1 -f -o gpurun_out/stress_k2c python tools/prof_run.py fast 3 1920 1080 2 1 4096 > gpurun_out/ncu_stress.log 2>&1; tail -3 gpurun_out/ncu_stress.log
+timeout -k 5 1500 python -m pytest tests -m gpu -q -rf > gpurun_out/pytest_full.log 2>&1; tail -6 gpurun_out/pytest_full.log
+timeout -k 5 600 python bench.py --steps 300 --warmup 10 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 3000 gpurun_out/bench_n1.json
+timeout -k 5 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
+timeout -k 5 300 python tools/fast_probe.py wave > gpurun_out/fast_probe_wave.log 2>&1
