@@ -341,7 +341,7 @@ int tpt_set_spp(tpt_context* ctx, int spp)
 int tpt_set_option(tpt_context* ctx, const char* key, int value)
 {
     if (!ctx || !key) return (int)cudaErrorInvalidValue;
-    if (!strcmp(key, "fast_variant")) { if (value < -1 || value > 8) return fail_msg(ctx, "fast_variant: -1 (auto), 0..8"); ctx->fastVariant = value; return 0; }
+    if (!strcmp(key, "fast_variant")) { if (value < -1 || value > 9) return fail_msg(ctx, "fast_variant: -1 (auto), 0..9"); ctx->fastVariant = value; return 0; }
     if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 8 && value != 9 && value != 32 && (value < 64 || value > 71)) return fail_msg(ctx, "exact_lanes: 0,1,2,8,9,32,64..71"); ctx->exactLanes = value; return 0; }
     if (!strcmp(key, "exact_lookahead")) { if (value < 0 || value > 256) return fail_msg(ctx, "exact_lookahead: 0..256"); ctx->exactLookahead = value; ctx->lookValid = false; return 0; }
     if (!strcmp(key, "register_host")) { ctx->registerHost = value ? 1 : 0; return 0; }
@@ -514,10 +514,10 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
     // Host-buffer fast draws: split the rows into bands, one stream per band (earlier band = higher priority). Each
     // stream runs prepare + trace for its band and then copies the band to the caller's buffer, so the D2H of band b
     // overlaps the tracing of band b+1 and the persistent CTAs of band b+1 fill the SMs as band b's tail drains.
-    bool pipelined = mode == TPT_MODE_FAST && !bufferOnDevice && fastVariant >= 3 && fastVariant <= 7 && ctx->hostBands > 1 &&
+    bool pipelined = mode == TPT_MODE_FAST && !bufferOnDevice && (fastVariant == 9 || (fastVariant >= 3 && fastVariant <= 7)) && ctx->hostBands > 1 &&
                      (rowStep == 1 || packed) && framesPerLaunch == numFrames && numRows >= 16 * ctx->hostBands;
     // the per-band completion counters are 32-bit (cuStreamWaitValue32): a band never holds more paths than the image
-    const bool progress = pipelined && ctx->waitValue32 && ctx->hostProgress && (fastVariant == 3 || fastVariant == 4) &&
+    const bool progress = pipelined && ctx->waitValue32 && ctx->hostProgress && (fastVariant == 3 || fastVariant == 4 || fastVariant == 9) &&
                           (long long)numRows * width * ctx->spp * numFrames <= 0xFFFFFFFFLL;
     if (progress)
     {

@@ -34,6 +34,49 @@ __device__ __forceinline__ uint32_t pixel_seed(uint32_t pixelIndex, uint32_t fra
 
 // Per-frame weights of the progressive blend (Test.cpp:272-276,293-295) when `numFrames` frames are fused in
 // one launch: image = prev*wPrev + sum_f mean_f * w[f], w[f] = (1-lerp_f) * prod_{g>f} lerp_g.
+// Fast mode draws its lens and roughness samples analytically instead of by rejection (Maths.cpp:20-37): the same
+// distributions (uniform on the unit disk / in the unit ball) from a fixed number of draws, so no lane of a warp waits in
+// a rejection loop for its neighbours (ncu: the two loops were 23 + ~25 warp instructions per path step at 18 / 3.5 active
+// lanes). The reference's own GPU ports sample analytically as well (ComputeShader.hlsl:18-35). TPT_FAST_ANALYTIC=0
+// restores the rejection loops for A/B runs.
+#ifndef TPT_FAST_ANALYTIC
+#define TPT_FAST_ANALYTIC 1
+#endif
+__device__ __forceinline__ V3 fast_in_unit_disk(uint32_t& state)
+{
+#if TPT_FAST_ANALYTIC
+    const float r = M<false>::sqrt_(RandomFloat01(state));
+    float sa, ca;
+    __sincosf(2.0f * TPT_PI * RandomFloat01(state), &sa, &ca);
+    return v3(r * ca, r * sa, 0.0f);
+#else
+    return RandomInUnitDisk(state);
+#endif
+}
+__device__ __forceinline__ V3 fast_in_unit_sphere(uint32_t& state)
+{
+#if TPT_FAST_ANALYTIC
+    const float z = 1.0f - 2.0f * RandomFloat01(state);
+    float sa, ca;
+    __sincosf(2.0f * TPT_PI * RandomFloat01(state), &sa, &ca);
+    const float rad = __powf(RandomFloat01(state), 1.0f / 3.0f);                 // radius = u^(1/3) as ex2(lg2(u)/3); u = 0 -> 0
+    const float r = M<false>::sqrt_(fmaxf(1.0f - z * z, 0.0f)) * rad;
+    return v3(r * ca, r * sa, z * rad);
+#else
+    return RandomInUnitSphere(state);
+#endif
+}
+// Maths.h:437-442 with the analytic lens sample
+__device__ __forceinline__ Ray fast_get_ray(const Camera88& c, float s, float t, uint32_t& state)
+{
+    V3 rd = c.lensRadius * fast_in_unit_disk(state);
+    V3 offset = ld3(c.uu) * rd.x + ld3(c.vv) * rd.y;
+    Ray r;
+    r.orig = ld3(c.origin) + offset;
+    r.dir = M<false>::normalize(ld3(c.lowerLeftCorner) + s * ld3(c.horizontal) + t * ld3(c.vertical) - ld3(c.origin) - offset);
+    return r;
+}
+
 __device__ __forceinline__ void blend_weights(const DrawParams& p, float* w, float& wPrev)
 {
     float suffix = 1.0f;
@@ -94,7 +137,7 @@ k_fast_mega(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayou
             {
                 float u = ((float)x + RandomFloat01(state)) * p.invWidth;
                 float v = ((float)y + RandomFloat01(state)) * p.invHeight;
-                Ray r = GetRay<false>(p.cam, u, v, state);
+                Ray r = fast_get_ray(p.cam, u, v, state);
                 col = col + trace_fast(sc, r, state, rc, hitter);
             }
             acc = acc + col * (invSpp * sW[fi]);
@@ -188,7 +231,7 @@ k_fast_persistent(DrawParams p, const unsigned char* __restrict__ blob, SceneBlo
                                             (uint32_t)(p.frame0 + fi));
                         float u = ((float)x + RandomFloat01(st.rng)) * p.invWidth;
                         float v = ((float)y + RandomFloat01(st.rng)) * p.invHeight;
-                        Ray r = GetRay<false>(p.cam, u, v, st.rng);
+                        Ray r = fast_get_ray(p.cam, u, v, st.rng);
                         st.o = r.orig; st.d = r.dir;
                         st.thr = v3(1, 1, 1); st.col = v3(0, 0, 0);
                         st.pix = pixIn; st.weight = invSpp * sW[fi];
@@ -335,6 +378,9 @@ constexpr int kSlabPix = TPT_SLAB_PIX;     // paths per slab (pixels x one sampl
 #define TPT_QUEUE_THREADS 128
 #define TPT_QUEUE_MINB 6
 #endif
+#ifndef TPT_P1_GROUP
+#define TPT_P1_GROUP 16
+#endif
 constexpr int kQueueThreads = TPT_QUEUE_THREADS;   // measured at 1280x720x4spp: 64 -> 20.33, 128 -> 20.33, 256 -> 20.46 Gray/s
 
 __global__ void k_prepare_image(DrawParams p, float wPrev)
@@ -368,7 +414,7 @@ __device__ __forceinline__ void generate_slab_rays(const DrawParams& p, float4 (
         uint32_t rng = pixel_seed((uint32_t)(y * p.width + x) * (uint32_t)p.spp + sample, frame);
         float u = ((float)x + RandomFloat01(rng)) * p.invWidth;
         float v = ((float)y + RandomFloat01(rng)) * p.invHeight;
-        Ray r = GetRay<false>(p.cam, u, v, rng);
+        Ray r = fast_get_ray(p.cam, u, v, rng);
         const uint32_t tag = tileBase < 0 ? (uint32_t)((p.packed ? ri : y) * p.width + x) : (uint32_t)tileBase + q;
         rays[q][0] = make_float4(r.orig.x, r.orig.y, r.orig.z, __uint_as_float(rng));
         rays[q][1] = make_float4(r.dir.x, r.dir.y, r.dir.z, __uint_as_float(tag));
@@ -512,6 +558,45 @@ struct FastHitterK2
         asm("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(xx), "=l"(yy) : "r"(sphP + (uint32_t)pair * 32u));
         asm("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(zz), "=l"(kk) : "r"(sphP + (uint32_t)pair * 32u + 16u));
     }
+    // pass 1 over spheres [s0, s0+G): G/2 packed pairs; shifts G rejection signs into `neg`
+    template <int G>
+    __device__ __forceinline__ void sweep_full(int s0, uint32_t& neg, unsigned long long DX, unsigned long long DY, unsigned long long DZ,
+                                               unsigned long long NOD, unsigned long long BX, unsigned long long BY, unsigned long long BZ,
+                                               unsigned long long NOO) const
+    {
+#pragma unroll
+        for (int j = 0; j < G; j += 2)
+        {
+            unsigned long long xx, yy, zz, kk;
+            ldp((s0 + j) >> 1, xx, yy, zz, kk);
+            const unsigned long long nb = f2_fma(xx, DX, f2_fma(yy, DY, f2_fma(zz, DZ, NOD)));
+            const unsigned long long negc = f2_fma(xx, BX, f2_fma(yy, BY, f2_fma(zz, BZ, f2_add(kk, NOO))));
+            const unsigned long long discr = f2_fma(nb, nb, negc);
+            // reject: discr < 0, or centre behind (nb < 0) with the origin outside (-c < 0)
+            const uint32_t r0 = (uint32_t)discr | ((uint32_t)nb & (uint32_t)negc);
+            const uint32_t r1 = (uint32_t)(discr >> 32) | ((uint32_t)(nb >> 32) & (uint32_t)(negc >> 32));
+            neg = __funnelshift_l(r0, neg, 1);
+            neg = __funnelshift_l(r1, neg, 1);
+        }
+    }
+    // The straight-line group between two (warp-uniform) bounds checks is the instruction scheduler's window: a group of 16
+    // spheres keeps eight independent packed chains in flight (measured at 1280x720x4spp: groups of 4 / 8 / 16 spheres ->
+    // 21.6 / 21.9 / 22.2 Gray/s). Counts that are not a multiple of the group fall through to halved groups, down to 4.
+    template <int G>
+    __device__ __forceinline__ void sweep_upto(int s0, int left, uint32_t& neg, unsigned long long DX, unsigned long long DY, unsigned long long DZ,
+                                               unsigned long long NOD, unsigned long long BX, unsigned long long BY, unsigned long long BZ,
+                                               unsigned long long NOO) const
+    {
+        if (left >= G) sweep_full<G>(s0, neg, DX, DY, DZ, NOD, BX, BY, BZ, NOO);
+        else if constexpr (G > 4)
+        {
+            if (left > 0)
+            {
+                sweep_upto<G / 2>(s0, left, neg, DX, DY, DZ, NOD, BX, BY, BZ, NOO);
+                sweep_upto<G / 2>(s0 + G / 2, left - G / 2, neg, DX, DY, DZ, NOD, BX, BY, BZ, NOO);
+            }
+        }
+    }
     __device__ __forceinline__ int hit(const SceneView&, V3 o, V3 d, float tMin, float tMax, float& tOut) const
     {
         const float nod = -fmaf(o.x, d.x, fmaf(o.y, d.y, o.z * d.z));
@@ -521,48 +606,44 @@ struct FastHitterK2
         const unsigned long long BX = f2_bcast(-ax), BY = f2_bcast(-ay), BZ = f2_bcast(-az), NOO = f2_bcast(-oo);
         float bestT = tMax;
         int bestId = -1;
-        for (int base = 0; base < simdCount; base += 32)
+        // chunks of 64 spheres: pass 1 fills a 64-bit candidate mask (sphere base + J <-> bit 63 - J), pass 2 walks it
+        for (int base = 0; base < simdCount; base += 64)
         {
-            const int n = simdCount - base < 32 ? simdCount - base : 32;     // multiple of 4
-            uint32_t neg = 0;
+            const int n = simdCount - base < 64 ? simdCount - base : 64;     // multiple of 4
+            const int n0 = n < 32 ? n : 32, n1 = n - n0;
+            uint32_t neg0 = 0, neg1 = 0;
 #pragma unroll
-            for (int k = 0; k < 32; k += 4)
+            for (int k = 0; k < 32; k += TPT_P1_GROUP) sweep_upto<TPT_P1_GROUP>(base + k, n0 - k, neg0, DX, DY, DZ, NOD, BX, BY, BZ, NOO);
+            if (n1 > 0)
             {
-                if (k < n)
-                {
 #pragma unroll
-                    for (int j = 0; j < 4; j += 2)
-                    {
-                        unsigned long long xx, yy, zz, kk;
-                        ldp((base + k + j) >> 1, xx, yy, zz, kk);
-                        const unsigned long long nb = f2_fma(xx, DX, f2_fma(yy, DY, f2_fma(zz, DZ, NOD)));
-                        const unsigned long long negc = f2_fma(xx, BX, f2_fma(yy, BY, f2_fma(zz, BZ, f2_add(kk, NOO))));
-                        const unsigned long long discr = f2_fma(nb, nb, negc);
-                        // reject: discr < 0, or centre behind (nb < 0) with the origin outside (-c < 0)
-                        const uint32_t r0 = (uint32_t)discr | ((uint32_t)nb & (uint32_t)negc);
-                        const uint32_t r1 = (uint32_t)(discr >> 32) | ((uint32_t)(nb >> 32) & (uint32_t)(negc >> 32));
-                        neg = __funnelshift_l(r0, neg, 1);
-                        neg = __funnelshift_l(r1, neg, 1);
-                    }
-                }
+                for (int k = 0; k < 32; k += TPT_P1_GROUP) sweep_upto<TPT_P1_GROUP>(base + 32 + k, n1 - k, neg1, DX, DY, DZ, NOD, BX, BY, BZ, NOO);
             }
-            uint32_t cand = ~neg & (n == 32 ? 0xffffffffu : ((1u << n) - 1u));
+            // left-align: after n shifts sphere j of the round sits at bit n-1-j
+            const uint32_t c0 = ~neg0 << (32 - n0);                                  // n0 >= 4
+            const uint32_t c1 = n1 > 0 ? ~neg1 << (32 - n1) : 0u;
+            unsigned long long cand = ((unsigned long long)c0 << 32) | c1;
+            // pass 2, two candidates per trip: the two evaluations (LDS.128, 9 FMA, MUFU.RSQ ...) are independent chains,
+            // so a trip costs one chain's latency instead of two; ascending sphere order as before
             while (cand)
             {
-                const int bit = 31 - __clz((int)cand);
-                cand &= ~(1u << bit);
-                const int i = base + (n - 1 - bit);
-                const float4 s = ld(i);
-                const float nb = fmaf(s.x, d.x, fmaf(s.y, d.y, fmaf(s.z, d.z, nod)));
-                const float c = fmaf(s.x, ax, fmaf(s.y, ay, fmaf(s.z, az, s.w + oo)));
-                const float discr = fmaf(nb, nb, -c);
-                if (discr > 0.0f)
-                {
-                    const float sq = M<false>::sqrt_(discr);
-                    float t = nb - sq;
-                    if (t <= tMin) t = nb + sq;
-                    if (t > tMin && t < bestT) { bestT = t; bestId = i; }
-                }
+                const int ja = __clzll((long long)cand);
+                cand &= ~(0x8000000000000000ull >> ja);
+                const bool hasB = cand != 0ull;
+                const int jb = hasB ? __clzll((long long)cand) : ja;
+                cand &= ~(0x8000000000000000ull >> jb);
+                const float4 sa = ld(base + ja), sb = ld(base + jb);
+                const float nba = fmaf(sa.x, d.x, fmaf(sa.y, d.y, fmaf(sa.z, d.z, nod)));
+                const float nbb = fmaf(sb.x, d.x, fmaf(sb.y, d.y, fmaf(sb.z, d.z, nod)));
+                const float ca = fmaf(sa.x, ax, fmaf(sa.y, ay, fmaf(sa.z, az, sa.w + oo)));
+                const float cb = fmaf(sb.x, ax, fmaf(sb.y, ay, fmaf(sb.z, az, sb.w + oo)));
+                const float da = fmaf(nba, nba, -ca), db = fmaf(nbb, nbb, -cb);
+                const float sqa = M<false>::sqrt_(fmaxf(da, 0.0f)), sqb = M<false>::sqrt_(fmaxf(db, 0.0f));
+                float ta = nba - sqa, tb = nbb - sqb;
+                if (ta <= tMin) ta = nba + sqa;
+                if (tb <= tMin) tb = nbb + sqb;
+                if (da > 0.0f && ta > tMin && ta < bestT) { bestT = ta; bestId = base + ja; }
+                if (hasB && db > 0.0f && tb > tMin && tb < bestT) { bestT = tb; bestId = base + jb; }
             }
         }
         tOut = bestT;
@@ -716,7 +797,7 @@ __device__ __forceinline__ bool path_step(const SceneView& sc, QPath& st, unsign
                     // Test.cpp:137-150; with roughness == 0 the unit-sphere sample has zero weight, so the fast
                     // mode skips drawing it (the exact mode must draw it: it advances the shared RNG stream)
                     V3 refl = reflect(st.d, normal);
-                    if (mat.roughness != 0.0f) refl = refl + mat.roughness * RandomInUnitSphere(st.rng);
+                    if (mat.roughness != 0.0f) refl = refl + mat.roughness * fast_in_unit_sphere(st.rng);
                     V3 outDir = M<false>::normalize(refl);
                     if (dot(outDir, normal) > 0.0f)
                     {
@@ -954,7 +1035,7 @@ __device__ __forceinline__ void generate_group_rays(const DrawParams& p, float4 
         uint32_t rng = pixel_seed((uint32_t)(y * p.width + x) * (uint32_t)p.spp + ss, (uint32_t)p.frame0 + fi);
         float u = ((float)x + RandomFloat01(rng)) * p.invWidth;
         float v = ((float)y + RandomFloat01(rng)) * p.invHeight;
-        Ray r = GetRay<false>(p.cam, u, v, rng);
+        Ray r = fast_get_ray(p.cam, u, v, rng);
         rays[q][0] = make_float4(r.orig.x, r.orig.y, r.orig.z, __uint_as_float(rng));
         rays[q][1] = make_float4(r.dir.x, r.dir.y, r.dir.z, __uint_as_float(px | (slot << 4) | (fi << 8)));
     }
@@ -1311,7 +1392,7 @@ k_fast_wave(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayou
                         uint32_t rng = pixel_seed((uint32_t)(y * p.width + (int)x) * (uint32_t)p.spp + ss, (uint32_t)p.frame0 + fi);
                         float u = ((float)x + RandomFloat01(rng)) * p.invWidth;
                         float v = ((float)y + RandomFloat01(rng)) * p.invHeight;
-                        Ray r = GetRay<false>(p.cam, u, v, rng);
+                        Ray r = fast_get_ray(p.cam, u, v, rng);
                         kind = 0; misc = 0 | (0 << 8) | (1 << 16);
                         fd = make_float4(r.dir.x, r.dir.y, r.dir.z, __int_as_float(misc));
                         WFLD(WF_O, tid) = make_float4(r.orig.x, r.orig.y, r.orig.z, 0.0f);
@@ -1423,7 +1504,7 @@ k_fast_wave(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayou
                             if (T == WT_METAL)
                             {
                                 V3 refl = reflect(d, normal);
-                                if (mat.roughness != 0.0f) refl = refl + mat.roughness * RandomInUnitSphere(rng);
+                                if (mat.roughness != 0.0f) refl = refl + mat.roughness * fast_in_unit_sphere(rng);
                                 outDir = M<false>::normalize(refl);
                                 att = mat.albedo;
                                 ok = dot(outDir, normal) > 0.0f;
@@ -1668,7 +1749,7 @@ int fast_queue_kform(const SceneDev& sc)
 
 int fast_slab_pixels() { return kSlabPix; }
 
-int fast_kernel_launches(const DrawParams&, int variant) { return (variant == 3 || variant == 4 || variant == 6 || variant == 7) ? 2 : 1; }
+int fast_kernel_launches(const DrawParams&, int variant) { return (variant == 3 || variant == 4 || variant == 9 || variant == 6 || variant == 7) ? 2 : 1; }
 bool fast_variant_writes_final_pixels(int variant) { return variant == 8; }
 
 
@@ -1704,7 +1785,7 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
         kern<<<grid, kFastThreads, sc.stagedBytes, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes, numTiles);
         return cudaGetLastError();
     }
-    if (variant == 3 || variant == 4)
+    if (variant == 3 || variant == 4 || variant == 9)
     {
         // sweep form: 2 = expanded + packed pairs (FFMA2; the pair array costs 16 B per sphere of extra shared memory) where
         // the scene passes the accuracy gate, 3 = the conservative packed form + reference-form pass 2 where it does not,
@@ -1717,7 +1798,12 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
         const bool big = stagedAl + ((kform >= 2) ? pairBytes : 0) + 4 * 2048 > 36 * 1024;
 #define TPT_LAUNCH_QUEUE(T, M, K) return launch_queue_t<T, M, K>(p, sc, numSMs, stream, bandDone, numBands, bandExpected)
         if (big) { switch (kform) { case 3: TPT_LAUNCH_QUEUE(768, 1, 3); case 2: TPT_LAUNCH_QUEUE(768, 1, 2); case 1: TPT_LAUNCH_QUEUE(768, 1, 1); default: TPT_LAUNCH_QUEUE(768, 1, 0); } }
-        if (variant == 3) { switch (kform) { case 3: TPT_LAUNCH_QUEUE(128, TPT_QUEUE_MINB, 3); case 2: TPT_LAUNCH_QUEUE(128, TPT_QUEUE_MINB, 2); case 1: TPT_LAUNCH_QUEUE(128, TPT_QUEUE_MINB, 1); default: TPT_LAUNCH_QUEUE(128, TPT_QUEUE_MINB, 0); } }
+        // long draws (many slabs per warp) run 8 CTAs of 64 registers per SM instead of 6 of 80: measured 26.2 vs 25.3 Gray/s at
+        // 3840x2160x16spp, but 21.6 vs 21.9 at 1280x720x4spp, where a warp only gets ~12 slabs and the drain of the last ones
+        // weighs more with more warps. Variant 9 forces the 8-CTA instance (A/B runs).
+        const long long slabsPerWarp = (((long long)p.numRows * p.width + kSlabPix - 1) / kSlabPix) * p.spp * p.numFrames / ((long long)numSMs * 32);
+        if (kform == 2 && (variant == 9 || (variant == 3 && slabsPerWarp >= 48))) TPT_LAUNCH_QUEUE(128, 8, 2);
+        if (variant == 3 || variant == 9) { switch (kform) { case 3: TPT_LAUNCH_QUEUE(128, TPT_QUEUE_MINB, 3); case 2: TPT_LAUNCH_QUEUE(128, TPT_QUEUE_MINB, 2); case 1: TPT_LAUNCH_QUEUE(128, TPT_QUEUE_MINB, 1); default: TPT_LAUNCH_QUEUE(128, TPT_QUEUE_MINB, 0); } }
         switch (kform) { case 3: TPT_LAUNCH_QUEUE(128, 7, 3); case 2: TPT_LAUNCH_QUEUE(128, 7, 2); case 1: TPT_LAUNCH_QUEUE(128, 7, 1); default: TPT_LAUNCH_QUEUE(128, 7, 0); }   // variant 4: 72 registers, 21.05 vs 21.14 Gray/s
 #undef TPT_LAUNCH_QUEUE
     }
