@@ -432,6 +432,21 @@ def main():
             line["exact_mode_lookahead16"] = {"value": la_rays / la_ms / 1e3, "unit": "Mray/s", "ms_per_step": la_ms / 32, "steps": 32,
                                               "note": "exact_lookahead = 16: amortised over 32 one-frame calls (2 trace launches of 16 "
                                                       "frames + 32 blends); first-call latency = 16 frames"}
+            # the drop-in's default (exact_lookahead = -1, adaptive): a fresh sequence of 64 one-frame calls INCLUDING the
+            # ramp-up (windows of 1, 2, 4, 8, 16, 16, 16 frames, then 1 frame of the next window of 16 -> 79 frames traced for
+            # 64 served; ray counts are those of the 64 frames handed out)
+            ctx.set_option("exact_lookahead", -1)
+            ev0.record(stream)
+            for s_ in range(64):
+                ctx.draw(1000 + s_, 1, W, H, image, flags=0, mode=tpt.MODE_EXACT, stream=sh, want_rays=False)
+            ev1.record(stream)
+            torch.cuda.synchronize(dev)
+            ad_rays = ctx.read_ray_count(sh)
+            ad_ms = ev0.elapsed_time(ev1)
+            ctx.set_option("exact_lookahead", 0)
+            line["exact_mode_adaptive"] = {"value": ad_rays / ad_ms / 1e3, "unit": "Mray/s", "ms_per_step": ad_ms / 64, "steps": 64,
+                                           "note": "exact_lookahead = -1 (what libtoytest_b200.so's DrawTest uses): 64 consecutive "
+                                                   "one-frame calls from a cold start, window doubling 1..16; no first-call latency"}
         if world == 1 and args.mode == "fast":
             # the reference-GPU-compatible estimator (per-pixel seeds, ComputeShader.hlsl) on the same frame: like for like
             # with the numbers the reference publishes for its own GPU back-ends (readme.md:64-77, other hardware)

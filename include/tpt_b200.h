@@ -65,8 +65,8 @@ int tpt_set_camera(tpt_context* ctx, const void* camera88);
 int tpt_set_spp(tpt_context* ctx, int spp);
 /* Implementation knobs (benchmarks/tests): "fast_variant" (-1 auto (default): 3 for device buffers (7 from 1024 spheres when the packed pair array does not fit in shared memory), 8 for host-buffer
  * draws that can store straight into page-locked memory; 0 megakernel, 1/2 persistent tiles, 3/4 persistent slab queue with 128-bit L2
- * reductions, 5 CTA-owned tiles, 6/7 block wavefront with material sort, 8 warp-owned pixel groups with coalesced 128-bit
- * write-out), "host_zero_copy" (default 1: with variant 8 a host-buffer draw whose `prev` has zero weight writes its finished
+ * reductions (3 picks its 8-CTA/SM 64-register instance by itself for long draws; 9 forces that instance), 5 CTA-owned tiles,
+ * 6/7 block wavefront with material sort, 8 warp-owned pixel groups with coalesced 128-bit write-out), "host_zero_copy" (default 1: with variant 8 a host-buffer draw whose `prev` has zero weight writes its finished
  * pixels directly into the caller's page-locked buffer over PCIe — no staging image, no device-to-host copy), "exact_lanes"
  * (0 auto; 64..67 = split kernel: one PATH warp per (frame,row) chain walks the RNG stream, 1..4 SHADE warps do the light
  * sampling / fold / blend off the critical path (auto for <= 2400 chains); 32 or 8 lanes per chain as nested loops; 1 = one
@@ -88,7 +88,9 @@ int tpt_set_spp(tpt_context* ctx, int spp);
  * single launch and keeps their per-frame colours; the calls for the following frames only blend their cached frame into
  * the caller's buffer. Bit-identical results and per-frame ray counts; trades L frames of latency on a miss for batch
  * throughput (one 720p frame alone cannot fill the GPU: `height` serial RNG chains). Never used with kFlagAnimate; any
- * scene / camera / size / row-range / spp change invalidates the cache),
+ * scene / camera / size / row-range / spp change invalidates the cache. -1 = adaptive: the first call traces one frame,
+ * and every time the caller has walked to the end of the cached window and asks for the frame right after it, the next
+ * window doubles (1, 2, 4, 8, 16 frames) — no first-call latency; the Test.h shim sets this, TPT_EXACT_LOOKAHEAD overrides),
  * "mitsuba_compare" (default 0; DO_MITSUBA_COMPARE of Config.h:25 as a runtime switch, applied by the NEXT
  * tpt_set_scene: constant sky (0.15, 0.21, 0.3) (Test.cpp:226-227) and zero Metal roughness (Test.cpp:143-145); the
  * switch's third effect, zero aperture (Test.cpp:312-313), is camera data: the Test.h shim's UpdateTest applies it). */

@@ -255,6 +255,45 @@ def test_frame_batches_limited_by_scratch(gpu_ctx, oracle):
     assert pf2 == r2 and not bits_differ(b2, o2, p2).any()
 
 
+def test_adaptive_frame_lookahead(libs, oracle):
+    """"exact_lookahead" = -1 (the drop-in's default): the window doubles (1, 2, 4, 8, 16) while the caller keeps asking for
+    the next frame and falls back to 1 after any break in the sequence; pixels and per-call ray counts stay those of
+    frame-by-frame draws."""
+    ctx = libs.Context(0)
+    sph, mats, cam, em = golden_scene()
+    w, h = 192, 108
+    ctx.set_scene(sph, mats, cam, em)
+    n = 40
+    ref = np.zeros((h, w, 4), np.float32)
+    ref_rays = [ctx.draw(f, 1, w, h, ref, flags=2, mode=0) for f in range(n)]
+    ctx.set_option("exact_lookahead", -1)
+    buf = np.zeros((h, w, 4), np.float32)
+    rays, launches = [], []
+    for f in range(n):
+        ctx.set_scene(sph, mats, cam, em)
+        rays.append(ctx.draw(f, 1, w, h, buf, flags=2, mode=0))
+        launches.append(ctx.last_launch_count())
+    assert rays == ref_rays and not bits_differ(buf, ref).any()
+    # trace launches happen at frames 0, 1, 3, 7, 15, 31 (windows of 1, 2, 4, 8, 16, 16): a miss that opens a window of more
+    # than one frame is trace + resolve + fold, a window of one is trace + fold, a hit resolve + fold
+    misses = [f for f in range(n) if launches[f] == 3 or f == 0]
+    assert misses == [0, 1, 3, 7, 15, 31], (misses, launches)
+    # a jump in the frame sequence and a camera change both restart at a window of one; results stay exact
+    cam2 = cam.copy(); cam2.view(np.float32)[0] += 0.25
+    a = np.zeros((h, w, 4), np.float32); b = np.zeros((h, w, 4), np.float32)
+    seq = [(50, cam), (51, cam), (52, cam), (60, cam), (61, cam2), (62, cam2), (63, cam2)]
+    ctx.set_option("exact_lookahead", 0)
+    ra = []
+    for f, c in seq:
+        ctx.set_scene(sph, mats, c, em); ra.append(ctx.draw(f, 1, w, h, a, flags=2, mode=0))
+    ctx.set_option("exact_lookahead", -1)
+    rb = []
+    for f, c in seq:
+        ctx.set_scene(sph, mats, c, em); rb.append(ctx.draw(f, 1, w, h, b, flags=2, mode=0))
+    assert ra == rb and not bits_differ(a, b).any()
+    ctx.close()
+
+
 def test_frame_lookahead_is_bit_identical(libs, oracle):
     """"exact_lookahead": a miss traces L frames in one launch, the following one-frame calls only blend their cached
     frame — same pixels, same per-frame ray counts as frame-by-frame draws; scene/camera/size changes invalidate."""

@@ -36,6 +36,9 @@ def run(case, w, h, nf, variant, reps, flags=0):
                       "mray_s": rays / tot / 1e3}), flush=True)
 
 
+frames = [int(v) for v in (sys.argv[4] if len(sys.argv) > 4 else "1").split(",")]
 for v in variants:
-    run("720p x4spp", 1280, 720, 1, v, reps)
-run("4K x16spp", 3840, 2160, 4, variants[0], max(reps // 20, 3), flags=2)
+    for nf in frames:
+        run("720p x%dspp" % (4 * nf), 1280, 720, nf, v, max(reps // nf, 3), flags=0 if nf == 1 else 2)
+if len(sys.argv) <= 5:
+    run("4K x16spp", 3840, 2160, 4, variants[0], max(reps // 20, 3), flags=2)

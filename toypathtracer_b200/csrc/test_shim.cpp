@@ -165,6 +165,10 @@ void InitializeTest()
     if (rc) die("tpt_create", rc);
     // A shell's backbuffer lives as long as the app (TestWin.cpp:73, Renderer.mm:148): page-locking it once lets
     // the per-frame copies run at full PCIe rate. Opt-in because the buffer must outlive the context.
+    // DrawTest is called frame after frame: in exact mode let consecutive calls share trace launches (adaptive frame
+    // lookahead, bit-identical pixels and ray counts; TPT_EXACT_LOOKAHEAD=0 switches it off, N > 1 fixes the window)
+    const char* la = getenv("TPT_EXACT_LOOKAHEAD");
+    tpt_set_option(s_Ctx, "exact_lookahead", la ? atoi(la) : -1);
     const char* pin = getenv("TPT_PIN_BACKBUFFER");
     if (pin && atoi(pin)) tpt_set_option(s_Ctx, "register_host", 1);
 }

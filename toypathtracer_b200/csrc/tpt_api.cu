@@ -56,7 +56,13 @@ struct tpt_context
     // blend their cached frame into the caller's buffer (per-frame colours do not depend on the buffer, Test.cpp:283-291):
     // same bits, same per-frame ray counts, L frames of latency on a miss. Not used under kFlagAnimate (the scene of a
     // future frame is not known yet); any scene, camera, size, row-range or spp change invalidates the cache.
+    // "exact_lookahead" = -1 is the adaptive form for callers that render frame after frame (the drop-in's DrawTest): the
+    // first call traces one frame; each time the caller walks to the end of the cached window and asks for the frame right
+    // after it, with nothing else changed, the next window doubles (1, 2, 4, 8, 16 frames). No first-call latency, at most
+    // half of the traced frames are speculative when the caller stops or changes anything.
     int exactLookahead = 0;
+    int lookLastServed = -1;        // last frame handed out from the current window
+    bool lookKeyValid = false;      // `look` describes the last one-frame exact draw (even a window of 1)
     struct LookKey { int frame0, n, width, height, row0, numRows, rowStep, spp; unsigned long long sceneGen; Camera88 cam; } look{};
     bool lookValid = false;
     float* dLook = nullptr; size_t lookCap = 0;
@@ -343,7 +349,7 @@ int tpt_set_option(tpt_context* ctx, const char* key, int value)
     if (!ctx || !key) return (int)cudaErrorInvalidValue;
     if (!strcmp(key, "fast_variant")) { if (value < -1 || value > 9) return fail_msg(ctx, "fast_variant: -1 (auto), 0..9"); ctx->fastVariant = value; return 0; }
     if (!strcmp(key, "exact_lanes")) { if (value != 0 && value != 1 && value != 2 && value != 8 && value != 9 && value != 32 && (value < 64 || value > 71)) return fail_msg(ctx, "exact_lanes: 0,1,2,8,9,32,64..71"); ctx->exactLanes = value; return 0; }
-    if (!strcmp(key, "exact_lookahead")) { if (value < 0 || value > 256) return fail_msg(ctx, "exact_lookahead: 0..256"); ctx->exactLookahead = value; ctx->lookValid = false; return 0; }
+    if (!strcmp(key, "exact_lookahead")) { if (value < -1 || value > 256) return fail_msg(ctx, "exact_lookahead: -1 (adaptive), 0..256"); ctx->exactLookahead = value; ctx->lookValid = false; ctx->lookKeyValid = false; return 0; }
     if (!strcmp(key, "register_host")) { ctx->registerHost = value ? 1 : 0; return 0; }
     if (!strcmp(key, "fast_kform")) { if (value < 0 || value > 2) return fail_msg(ctx, "fast_kform: 0..2"); ctx->fastKForm = value; return 0; }
     if (!strcmp(key, "fast_alpha_zero")) { ctx->fastAlphaZero = value ? 1 : 0; return 0; }
@@ -580,7 +586,7 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
         p.frame0 = frameCount + f;
         p.numFrames = nf;
         cudaError_t e;
-        if (mode == TPT_MODE_EXACT && numFrames == 1 && ctx->exactLookahead > 1 && !(testFlags & TPT_FLAG_ANIMATE))
+        if (mode == TPT_MODE_EXACT && numFrames == 1 && (ctx->exactLookahead > 1 || ctx->exactLookahead == -1) && !(testFlags & TPT_FLAG_ANIMATE))
         {
             // frame lookahead (see tpt_context::exactLookahead)
             tpt_context::LookKey k{};
@@ -588,12 +594,15 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
             k.sceneGen = ctx->sceneGen; k.cam = ctx->cam;
             const tpt_context::LookKey& c = ctx->look;
             const size_t perFrame = (size_t)numRows * width * 4;           // floats
-            const bool hit = ctx->lookValid && frameCount >= c.frame0 && frameCount < c.frame0 + c.n && c.width == k.width &&
-                             c.height == k.height && c.row0 == k.row0 && c.numRows == k.numRows && c.rowStep == k.rowStep &&
-                             c.spp == k.spp && c.sceneGen == k.sceneGen && !memcmp(&c.cam, &k.cam, sizeof(Camera88));
+            const bool sameSetup = c.width == k.width && c.height == k.height && c.row0 == k.row0 && c.numRows == k.numRows &&
+                                   c.rowStep == k.rowStep && c.spp == k.spp && c.sceneGen == k.sceneGen && !memcmp(&c.cam, &k.cam, sizeof(Camera88));
+            const bool hit = ctx->lookValid && frameCount >= c.frame0 && frameCount < c.frame0 + c.n && sameSetup;
             if (!hit)
             {
-                size_t L = (size_t)ctx->exactLookahead;
+                size_t L = ctx->exactLookahead > 1 ? (size_t)ctx->exactLookahead : 1;
+                if (ctx->exactLookahead == -1 && ctx->lookKeyValid && sameSetup && frameCount == c.frame0 + c.n &&
+                    ctx->lookLastServed == c.frame0 + c.n - 1)
+                    L = c.n >= 8 ? 16 : (size_t)c.n * 2;           // the caller consumed the whole window and continues: double it
                 const size_t fit = ctx->maxScratchBytes / (perFrame * 4);
                 if (L > fit) L = fit < 1 ? 1 : fit;
                 int r = ensure(ctx, (void**)&ctx->dLook, &ctx->lookCap, L * perFrame * 4, "cudaMalloc lookahead cache");
@@ -607,10 +616,11 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
                 if (e != cudaSuccess) return fail(ctx, e, "kernel launch");
                 ctx->lastLaunches += 1;
                 k.frame0 = frameCount; k.n = (int)L;
-                ctx->look = k; ctx->lookValid = L > 1;
+                ctx->look = k; ctx->lookValid = L > 1; ctx->lookKeyValid = true; ctx->lookLastServed = frameCount;
                 if (L == 1) { CK(cudaMemcpyAsync(ctx->dRayCounters, ctx->dLookRays, 8, cudaMemcpyDeviceToDevice, stream), "counter copy"); continue; }
             }
             const int i = frameCount - ctx->look.frame0;
+            ctx->lookLastServed = frameCount;
             DrawParams pr = p;
             pr.frame0 = frameCount; pr.numFrames = 1; pr.scratch = ctx->dLook + (size_t)i * perFrame;
             e = launch_resolve_exact(pr, stream);

@@ -82,11 +82,14 @@ __device__ __forceinline__ void stage_blob(unsigned char* dst, const unsigned ch
 }
 
 // Scene view: sections inside the staged prefix point to shared memory, the rest to global memory.
+// ALL_STAGED: the caller guarantees stagedBytes == L.totalBytes; every pointer is then derived from the shared-memory base
+// alone, which lets the compiler prove the address space (LDS instead of generic LD with 64-bit address arithmetic).
+template <bool ALL_STAGED = false>
 __device__ __forceinline__ SceneView make_view(const unsigned char* smemBase, const unsigned char* globalBase,
                                                const SceneBlobLayout& L, uint32_t stagedBytes, int count, int nLights)
 {
     SceneView v;
-    auto pick = [&](uint32_t off) -> const unsigned char* { return off < stagedBytes ? smemBase + off : globalBase + off; };
+    auto pick = [&](uint32_t off) -> const unsigned char* { return (ALL_STAGED || off < stagedBytes) ? smemBase + off : globalBase + off; };
     v.sph = (const Q4*)pick(L.offSph);
     v.invRadius = (const float*)pick(L.offInvRadius);
     v.lights = (const LightRec*)pick(L.offLights);

@@ -11,6 +11,9 @@
 //            path ends (ray regeneration), so the ray-vs-all-spheres sweep — 85 % of the instructions — always
 //            runs with full warps. Radiance is accumulated per pixel in shared memory; finished tiles are
 //            written with coalesced 128-bit stores (and 128-bit loads of `prev` when accumulating).
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 #include "tpt_integrator.cuh"
 #include "tpt_device_utils.cuh"
 #include "tpt_launch.h"
@@ -42,6 +45,7 @@ __device__ __forceinline__ uint32_t pixel_seed(uint32_t pixelIndex, uint32_t fra
 #ifndef TPT_FAST_ANALYTIC
 #define TPT_FAST_ANALYTIC 1
 #endif
+__device__ __forceinline__ int opaque_int(int x) { asm volatile("" : "+r"(x)); return x; }
 __device__ __forceinline__ V3 fast_in_unit_disk(uint32_t& state)
 {
 #if TPT_FAST_ANALYTIC
@@ -779,8 +783,11 @@ __device__ __forceinline__ bool path_step(const SceneView& sc, QPath& st, unsign
                 V3 normal = (pos - v3(s.x, s.y, s.z)) * sc.invRadius[id];
                 const int mid = id < sc.count ? id : sc.count;
                 Mat mat = load_mat(sc, mid);
+                // the compiler turns a three-way test of mat.type into a jump table (LDC from the constant bank + BRX: two
+                // long-latency steps in front of every shading branch); keeping the second test opaque keeps it two branches
+                int mtype = mat.type;
                 if (st.depth >= TPT_MAX_DEPTH) { st.col = st.col + st.thr * mat.emissive; finished = true; }
-                else if (mat.type == kLambert)
+                else if (mtype == kLambert)
                 {
                     if (st.doMaterialE) st.col = st.col + st.thr * mat.emissive;
                     V3 target = normal + RandomUnitVector<false>(st.rng);
@@ -792,7 +799,7 @@ __device__ __forceinline__ bool path_step(const SceneView& sc, QPath& st, unsign
                     st.o = pos;
                     wantLight = true; lightFrom = 0;
                 }
-                else if (mat.type == kMetal)
+                else if (opaque_int(mtype) == kMetal)
                 {
                     // Test.cpp:137-150; with roughness == 0 the unit-sphere sample has zero weight, so the fast
                     // mode skips drawing it (the exact mode must draw it: it advances the shared RNG stream)
@@ -840,12 +847,12 @@ __device__ __forceinline__ bool path_step(const SceneView& sc, QPath& st, unsign
             V3 scn = v3(Lr.cx, Lr.cy, Lr.cz);
             V3 pc = scn - st.o;
             float d2 = dot(pc, pc);
-            float inv = rsqrtf(d2);
+            float inv = __frsqrt_rn(d2);          // d2 is a squared distance between distinct spheres: never denormal
             V3 sw = pc * inv;
             // any orthonormal (su, sv) around sw gives the same cone-sample distribution (phi is uniform): use the
             // branch-free basis of Duff et al. 2017 instead of normalize(cross(up, sw)), cross(sw, su) (Test.cpp:108-109)
             const float sgn = copysignf(1.0f, sw.z);
-            const float oa = -1.0f / (sgn + sw.z);
+            const float oa = __fdividef(-1.0f, sgn + sw.z);      // |sgn + sw.z| in [1, 2]: MUFU.RCP + FMUL instead of the IEEE sequence
             const float ob = sw.x * sw.y * oa;
             V3 su = v3(1.0f + sgn * sw.x * sw.x * oa, sgn * ob, -sgn * sw.x);
             V3 sv = v3(ob, sgn + sw.y * sw.y * oa, -sw.y);
@@ -876,6 +883,17 @@ __device__ __forceinline__ bool path_step(const SceneView& sc, QPath& st, unsign
     return finished;
 }
 
+// Diagnostic build (-DTPT_TRACE_WARPS=1, tools/warp_trace.py): every warp of k_fast_queue records global-timer stamps (entry,
+// first slab, queue exhausted, exit), its trip counts and the lane-slots it used after the queue ran dry: the kernel's
+// end effects (fill, drain, stragglers) measured instead of guessed. Not compiled into the shipped library.
+#ifndef TPT_TRACE_WARPS
+#define TPT_TRACE_WARPS 0
+#endif
+#if TPT_TRACE_WARPS
+__device__ unsigned long long* g_warpTrace = nullptr;
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#endif
+
 // KFORM 0: reference-form sweep, 1: expanded form, 2: expanded form on packed pairs (FFMA2), 3: packed-pair pass 1 made
 // conservative + reference-form pass 2 (FastHitterK2C: any scene). THREADS: 128 (6 CTAs/SM) for scenes whose staged
 // geometry is small; one big CTA per SM when the sphere arrays fill most of an SM's shared memory.
@@ -892,9 +910,16 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
     // camera rays of the warp's current slab, generated 4 per lane in one convergent burst when the slab is fetched:
     // {origin.xyz, rng state} {direction.xyz, pixel offset}; regeneration then only pops an entry.
     float4 (*sRays)[kSlabPix][2] = reinterpret_cast<float4 (*)[kSlabPix][2]>(smem + raysOffset);
+#if TPT_TRACE_WARPS
+    const unsigned long long trEntry = gtimer();
+    unsigned long long trReady = 0, trDry = 0;
+    unsigned trTrips = 0, trDryTrips = 0, trDryLanes = 0;
+#endif
     stage_blob(smem, blob, stagedBytes, &bar);
     if (threadIdx.x == 0) { float wp; blend_weights(p, sW, wp); }
-    SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
+    // the 128-thread instances are only launched for scenes whose whole blob is staged (launch_fast): their view points into
+    // shared memory for every section, so materials, lights and 1/r load with LDS instead of generic LD
+    SceneView sc = make_view<THREADS == 128>(smem, blob, L, stagedBytes, count, nLights);
     float4* sphK = reinterpret_cast<float4*>(smem + L.offSph);
     if (KFORM == 1 || KFORM == 2) build_sphK(sc, sphK);
     __syncthreads();
@@ -985,6 +1010,11 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
             need = __ballot_sync(0xffffffffu, !st.active);
         }
         if (!__any_sync(0xffffffffu, st.active)) break;
+#if TPT_TRACE_WARPS
+        if (!trReady) trReady = gtimer();
+        ++trTrips;
+        if (exhausted) { if (!trDry) trDry = gtimer(); ++trDryTrips; trDryLanes += (unsigned)__popc(__ballot_sync(0xffffffffu, st.active)); }
+#endif
 
         const bool finished = KFORM == 3 ? path_step(sc, st, rc, hitK2C) : KFORM == 2 ? path_step(sc, st, rc, hitK2) : (KFORM == 1 ? path_step(sc, st, rc, hitK) : path_step(sc, st, rc, hitS));
         if (finished)
@@ -1005,6 +1035,14 @@ k_fast_queue(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
     if (bandDone && doneCnt) { __threadfence(); atomicAdd(bandDone + curBand, doneCnt); }
     for (int off = 16; off > 0; off >>= 1) rc += __shfl_xor_sync(0xffffffffu, rc, off);
     if (lane == 0 && rc) atomicAdd(p.rayCounter, (unsigned long long)rc);
+#if TPT_TRACE_WARPS
+    if (lane == 0 && g_warpTrace)
+    {
+        unsigned smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        unsigned long long* t = g_warpTrace + ((size_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5)) * 8;
+        t[0] = trEntry; t[1] = trReady; t[2] = trDry; t[3] = gtimer(); t[4] = trTrips; t[5] = trDryTrips; t[6] = trDryLanes; t[7] = smid;
+    }
+#endif
 }
 
 // ---- variant 8 ------------------------------------------------------------------------------------------------
@@ -1682,8 +1720,26 @@ static cudaError_t launch_queue_t(const DrawParams& p, const SceneDev& sc, int n
             bandExpected[b] = (unsigned int)(px * S);
         }
     }
+#if TPT_TRACE_WARPS
+    static unsigned long long* dTrace = nullptr;
+    const size_t traceWords = (size_t)grid * (THREADS / 32) * 8;
+    if (getenv("TPT_TRACE_FILE"))
+    {
+        if (!dTrace) { cudaMalloc(&dTrace, (size_t)148 * 16 * 32 * 8 * 8); cudaMemcpyToSymbol(g_warpTrace, &dTrace, sizeof(dTrace)); }
+        cudaMemsetAsync(dTrace, 0, traceWords * 8, stream);
+    }
+#endif
     kern<<<(unsigned)grid, THREADS, dyn3, stream>>>(p, sc.blob, sc.layout, sc.count, sc.nLights, sc.stagedBytes,
                                                       (uint32_t)slabs, S, mpb ? bandDone : nullptr, mpb ? mpb : 1u, (uint32_t)raysOffset);
+#if TPT_TRACE_WARPS
+    if (const char* tf = getenv("TPT_TRACE_FILE"))
+    {
+        cudaStreamSynchronize(stream);
+        std::vector<unsigned long long> h(traceWords);
+        cudaMemcpy(h.data(), dTrace, traceWords * 8, cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(tf, "wb")) { fwrite(h.data(), 8, traceWords, f); fclose(f); }     // the last traced launch wins
+    }
+#endif
     return cudaGetLastError();
 }
 
@@ -1795,7 +1851,7 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
         const int kform = fast_queue_kform(sc);
         // small scenes: 128-thread CTAs, 6 (variant 4: 7) per SM; scenes whose arrays fill most of an SM's shared memory: ONE
         // 768-thread CTA per SM (24 warps share one copy of the geometry instead of 2 CTAs x 4 warps with a copy each)
-        const bool big = stagedAl + ((kform >= 2) ? pairBytes : 0) + 4 * 2048 > 36 * 1024;
+        const bool big = stagedAl + ((kform >= 2) ? pairBytes : 0) + 4 * 2048 > 36 * 1024 || sc.stagedBytes != sc.layout.totalBytes;
 #define TPT_LAUNCH_QUEUE(T, M, K) return launch_queue_t<T, M, K>(p, sc, numSMs, stream, bandDone, numBands, bandExpected)
         if (big) { switch (kform) { case 3: TPT_LAUNCH_QUEUE(768, 1, 3); case 2: TPT_LAUNCH_QUEUE(768, 1, 2); case 1: TPT_LAUNCH_QUEUE(768, 1, 1); default: TPT_LAUNCH_QUEUE(768, 1, 0); } }
         // long draws (many slabs per warp) run 8 CTAs of 64 registers per SM instead of 6 of 80: measured 26.2 vs 25.3 Gray/s at
