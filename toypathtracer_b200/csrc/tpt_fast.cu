@@ -546,6 +546,62 @@ __device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsig
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// Packed-pair pass 1 shared by FastHitterK2 / FastHitterK2C: spheres [s0, s0+G) = G/2 pairs of the pair array at shared
+// address sphP; shifts G rejection signs into `neg` (sphere s0 ends up at the highest of the G new bits).
+struct SweepConsts { unsigned long long DX, DY, DZ, NOD, BX, BY, BZ, NOO; };
+template <int G>
+__device__ __forceinline__ void sweep_full(uint32_t sphP, int s0, uint32_t& neg, const SweepConsts& c)
+{
+#pragma unroll
+    for (int j = 0; j < G; j += 2)
+    {
+        unsigned long long xx, yy, zz, kk;
+        const uint32_t a = sphP + (uint32_t)((s0 + j) >> 1) * 32u;
+        asm("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(xx), "=l"(yy) : "r"(a));
+        asm("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(zz), "=l"(kk) : "r"(a + 16u));
+        const unsigned long long nb = f2_fma(xx, c.DX, f2_fma(yy, c.DY, f2_fma(zz, c.DZ, c.NOD)));
+        const unsigned long long negc = f2_fma(xx, c.BX, f2_fma(yy, c.BY, f2_fma(zz, c.BZ, f2_add(kk, c.NOO))));
+        const unsigned long long discr = f2_fma(nb, nb, negc);
+        // reject: discr < 0, or centre behind (nb < 0) with the origin outside (-c < 0)
+        const uint32_t r0 = (uint32_t)discr | ((uint32_t)nb & (uint32_t)negc);
+        const uint32_t r1 = (uint32_t)(discr >> 32) | ((uint32_t)(nb >> 32) & (uint32_t)(negc >> 32));
+        neg = __funnelshift_l(r0, neg, 1);
+        neg = __funnelshift_l(r1, neg, 1);
+    }
+}
+// The straight-line group between two (warp-uniform) bounds checks is the instruction scheduler's window: a group of 16
+// spheres keeps eight independent packed chains in flight (measured at 1280x720x4spp: groups of 4 / 8 / 16 spheres ->
+// 21.6 / 21.9 / 22.2 Gray/s). Counts that are not a multiple of the group fall through to halved groups, down to 4.
+template <int G>
+__device__ __forceinline__ void sweep_upto(uint32_t sphP, int s0, int left, uint32_t& neg, const SweepConsts& c)
+{
+    if (left >= G) sweep_full<G>(sphP, s0, neg, c);
+    else if constexpr (G > 4)
+    {
+        if (left > 0)
+        {
+            sweep_upto<G / 2>(sphP, s0, left, neg, c);
+            sweep_upto<G / 2>(sphP, s0 + G / 2, left - G / 2, neg, c);
+        }
+    }
+}
+// 64 spheres [base, base+n) -> candidate mask, sphere base + J <-> bit 63 - J (n a multiple of 4, 4 <= n <= 64)
+__device__ __forceinline__ unsigned long long sweep_chunk64(uint32_t sphP, int base, int n, const SweepConsts& c)
+{
+    const int n0 = n < 32 ? n : 32, n1 = n - n0;
+    uint32_t neg0 = 0, neg1 = 0;
+#pragma unroll
+    for (int k = 0; k < 32; k += TPT_P1_GROUP) sweep_upto<TPT_P1_GROUP>(sphP, base + k, n0 - k, neg0, c);
+    if (n1 > 0)
+    {
+#pragma unroll
+        for (int k = 0; k < 32; k += TPT_P1_GROUP) sweep_upto<TPT_P1_GROUP>(sphP, base + 32 + k, n1 - k, neg1, c);
+    }
+    // left-align: after n shifts sphere j of the round sits at bit n-1-j
+    const uint32_t c0 = ~neg0 << (32 - n0);
+    const uint32_t c1 = n1 > 0 ? ~neg1 << (32 - n1) : 0u;
+    return ((unsigned long long)c0 << 32) | c1;
+}
 struct FastHitterK2
 {
     uint32_t sphK;      // shared-memory address of {sx, sy, sz, K}[simdCount]         (pass 2)
@@ -562,73 +618,21 @@ struct FastHitterK2
         asm("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(xx), "=l"(yy) : "r"(sphP + (uint32_t)pair * 32u));
         asm("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(zz), "=l"(kk) : "r"(sphP + (uint32_t)pair * 32u + 16u));
     }
-    // pass 1 over spheres [s0, s0+G): G/2 packed pairs; shifts G rejection signs into `neg`
-    template <int G>
-    __device__ __forceinline__ void sweep_full(int s0, uint32_t& neg, unsigned long long DX, unsigned long long DY, unsigned long long DZ,
-                                               unsigned long long NOD, unsigned long long BX, unsigned long long BY, unsigned long long BZ,
-                                               unsigned long long NOO) const
-    {
-#pragma unroll
-        for (int j = 0; j < G; j += 2)
-        {
-            unsigned long long xx, yy, zz, kk;
-            ldp((s0 + j) >> 1, xx, yy, zz, kk);
-            const unsigned long long nb = f2_fma(xx, DX, f2_fma(yy, DY, f2_fma(zz, DZ, NOD)));
-            const unsigned long long negc = f2_fma(xx, BX, f2_fma(yy, BY, f2_fma(zz, BZ, f2_add(kk, NOO))));
-            const unsigned long long discr = f2_fma(nb, nb, negc);
-            // reject: discr < 0, or centre behind (nb < 0) with the origin outside (-c < 0)
-            const uint32_t r0 = (uint32_t)discr | ((uint32_t)nb & (uint32_t)negc);
-            const uint32_t r1 = (uint32_t)(discr >> 32) | ((uint32_t)(nb >> 32) & (uint32_t)(negc >> 32));
-            neg = __funnelshift_l(r0, neg, 1);
-            neg = __funnelshift_l(r1, neg, 1);
-        }
-    }
-    // The straight-line group between two (warp-uniform) bounds checks is the instruction scheduler's window: a group of 16
-    // spheres keeps eight independent packed chains in flight (measured at 1280x720x4spp: groups of 4 / 8 / 16 spheres ->
-    // 21.6 / 21.9 / 22.2 Gray/s). Counts that are not a multiple of the group fall through to halved groups, down to 4.
-    template <int G>
-    __device__ __forceinline__ void sweep_upto(int s0, int left, uint32_t& neg, unsigned long long DX, unsigned long long DY, unsigned long long DZ,
-                                               unsigned long long NOD, unsigned long long BX, unsigned long long BY, unsigned long long BZ,
-                                               unsigned long long NOO) const
-    {
-        if (left >= G) sweep_full<G>(s0, neg, DX, DY, DZ, NOD, BX, BY, BZ, NOO);
-        else if constexpr (G > 4)
-        {
-            if (left > 0)
-            {
-                sweep_upto<G / 2>(s0, left, neg, DX, DY, DZ, NOD, BX, BY, BZ, NOO);
-                sweep_upto<G / 2>(s0 + G / 2, left - G / 2, neg, DX, DY, DZ, NOD, BX, BY, BZ, NOO);
-            }
-        }
-    }
     __device__ __forceinline__ int hit(const SceneView&, V3 o, V3 d, float tMin, float tMax, float& tOut) const
     {
         const float nod = -fmaf(o.x, d.x, fmaf(o.y, d.y, o.z * d.z));
         const float oo = fmaf(o.x, o.x, fmaf(o.y, o.y, o.z * o.z));
         const float ax = -2.0f * o.x, ay = -2.0f * o.y, az = -2.0f * o.z;
-        const unsigned long long DX = f2_bcast(d.x), DY = f2_bcast(d.y), DZ = f2_bcast(d.z), NOD = f2_bcast(nod);
-        const unsigned long long BX = f2_bcast(-ax), BY = f2_bcast(-ay), BZ = f2_bcast(-az), NOO = f2_bcast(-oo);
+        SweepConsts C;
+        C.DX = f2_bcast(d.x); C.DY = f2_bcast(d.y); C.DZ = f2_bcast(d.z); C.NOD = f2_bcast(nod);
+        C.BX = f2_bcast(-ax); C.BY = f2_bcast(-ay); C.BZ = f2_bcast(-az); C.NOO = f2_bcast(-oo);
         float bestT = tMax;
         int bestId = -1;
         // chunks of 64 spheres: pass 1 fills a 64-bit candidate mask (sphere base + J <-> bit 63 - J), pass 2 walks it
         for (int base = 0; base < simdCount; base += 64)
         {
-            const int n = simdCount - base < 64 ? simdCount - base : 64;     // multiple of 4
-            const int n0 = n < 32 ? n : 32, n1 = n - n0;
-            uint32_t neg0 = 0, neg1 = 0;
-#pragma unroll
-            for (int k = 0; k < 32; k += TPT_P1_GROUP) sweep_upto<TPT_P1_GROUP>(base + k, n0 - k, neg0, DX, DY, DZ, NOD, BX, BY, BZ, NOO);
-            if (n1 > 0)
-            {
-#pragma unroll
-                for (int k = 0; k < 32; k += TPT_P1_GROUP) sweep_upto<TPT_P1_GROUP>(base + 32 + k, n1 - k, neg1, DX, DY, DZ, NOD, BX, BY, BZ, NOO);
-            }
-            // left-align: after n shifts sphere j of the round sits at bit n-1-j
-            const uint32_t c0 = ~neg0 << (32 - n0);                                  // n0 >= 4
-            const uint32_t c1 = n1 > 0 ? ~neg1 << (32 - n1) : 0u;
-            unsigned long long cand = ((unsigned long long)c0 << 32) | c1;
-            // pass 2, two candidates per trip: the two evaluations (LDS.128, 9 FMA, MUFU.RSQ ...) are independent chains,
-            // so a trip costs one chain's latency instead of two; ascending sphere order as before
+            unsigned long long cand = sweep_chunk64(sphP, base, simdCount - base < 64 ? simdCount - base : 64, C);
+            // pass 2, two candidates per trip (independent LDS.128 / 9 FMA / MUFU chains); ascending sphere order as before
             while (cand)
             {
                 const int ja = __clzll((long long)cand);
@@ -674,54 +678,34 @@ struct FastHitterK2C
     {
         const float nod = -fmaf(o.x, d.x, fmaf(o.y, d.y, o.z * d.z));
         const float oo = fmaf(o.x, o.x, fmaf(o.y, o.y, o.z * o.z));
-        const unsigned long long DX = f2_bcast(d.x), DY = f2_bcast(d.y), DZ = f2_bcast(d.z), NOD = f2_bcast(nod);
-        const unsigned long long BX = f2_bcast(2.0f * o.x), BY = f2_bcast(2.0f * o.y), BZ = f2_bcast(2.0f * o.z);
-        const unsigned long long NOO = f2_bcast(oo * 7.62939453125e-6f - oo);     // the ray's share of the margin: 2^-17 o.o
+        SweepConsts C;
+        C.DX = f2_bcast(d.x); C.DY = f2_bcast(d.y); C.DZ = f2_bcast(d.z); C.NOD = f2_bcast(nod);
+        C.BX = f2_bcast(2.0f * o.x); C.BY = f2_bcast(2.0f * o.y); C.BZ = f2_bcast(2.0f * o.z);
+        C.NOO = f2_bcast(oo * 7.62939453125e-6f - oo);     // the ray's share of the margin: 2^-17 o.o
         float bestT = tMax;
         int bestId = -1;
-        for (int base = 0; base < simdCount; base += 32)
+        for (int base = 0; base < simdCount; base += 64)
         {
-            const int n = simdCount - base < 32 ? simdCount - base : 32;
-            uint32_t neg = 0;
-#pragma unroll
-            for (int k = 0; k < 32; k += 4)
-            {
-                if (k < n)
-                {
-#pragma unroll
-                    for (int j = 0; j < 4; j += 2)
-                    {
-                        unsigned long long xx, yy, zz, kk;
-                        const uint32_t a = sphP + (uint32_t)((base + k + j) >> 1) * 32u;
-                        asm("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(xx), "=l"(yy) : "r"(a));
-                        asm("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(zz), "=l"(kk) : "r"(a + 16u));
-                        const unsigned long long nb = f2_fma(xx, DX, f2_fma(yy, DY, f2_fma(zz, DZ, NOD)));
-                        const unsigned long long negc = f2_fma(xx, BX, f2_fma(yy, BY, f2_fma(zz, BZ, f2_add(kk, NOO))));
-                        const unsigned long long discr = f2_fma(nb, nb, negc);
-                        const uint32_t r0 = (uint32_t)discr | ((uint32_t)nb & (uint32_t)negc);
-                        const uint32_t r1 = (uint32_t)(discr >> 32) | ((uint32_t)(nb >> 32) & (uint32_t)(negc >> 32));
-                        neg = __funnelshift_l(r0, neg, 1);
-                        neg = __funnelshift_l(r1, neg, 1);
-                    }
-                }
-            }
-            uint32_t cand = ~neg & (n == 32 ? 0xffffffffu : ((1u << n) - 1u));
+            unsigned long long cand = sweep_chunk64(sphP, base, simdCount - base < 64 ? simdCount - base : 64, C);
+            // pass 2 on the untouched {s, r^2} array in the reference form (Maths.cpp:97-102), two candidates per trip
             while (cand)
             {
-                const int bit = 31 - __clz((int)cand);
-                cand &= ~(1u << bit);
-                const int i = base + (n - 1 - bit);
-                Q4 s;
-                asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(s.x), "=f"(s.y), "=f"(s.z), "=f"(s.w) : "r"(sph + (uint32_t)i * 16u));
-                float nb;
-                const float discr = sphere_discr<false>(s, o, d, nb);         // reference form
-                if (discr > 0.0f)
-                {
-                    const float sq = M<false>::sqrt_(discr);
-                    float t = nb - sq;
-                    if (t <= tMin) t = nb + sq;
-                    if (t > tMin && t < bestT) { bestT = t; bestId = i; }
-                }
+                const int ja = __clzll((long long)cand);
+                cand &= ~(0x8000000000000000ull >> ja);
+                const bool hasB = cand != 0ull;
+                const int jb = hasB ? __clzll((long long)cand) : ja;
+                cand &= ~(0x8000000000000000ull >> jb);
+                Q4 sa, sb;
+                asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(sa.x), "=f"(sa.y), "=f"(sa.z), "=f"(sa.w) : "r"(sph + (uint32_t)(base + ja) * 16u));
+                asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(sb.x), "=f"(sb.y), "=f"(sb.z), "=f"(sb.w) : "r"(sph + (uint32_t)(base + jb) * 16u));
+                float nba, nbb;
+                const float da = sphere_discr<false>(sa, o, d, nba), db = sphere_discr<false>(sb, o, d, nbb);
+                const float sqa = M<false>::sqrt_(fmaxf(da, 0.0f)), sqb = M<false>::sqrt_(fmaxf(db, 0.0f));
+                float ta = nba - sqa, tb = nbb - sqb;
+                if (ta <= tMin) ta = nba + sqa;
+                if (tb <= tMin) tb = nbb + sqb;
+                if (da > 0.0f && ta > tMin && ta < bestT) { bestT = ta; bestId = base + ja; }
+                if (hasB && db > 0.0f && tb > tMin && tb < bestT) { bestT = tb; bestId = base + jb; }
             }
         }
         tOut = bestT;
@@ -1079,7 +1063,7 @@ __device__ __forceinline__ void generate_group_rays(const DrawParams& p, float4 
     }
 }
 
-template <int MINB, int KFORM>
+template <int MINB, int KFORM, bool ALLS>
 __global__ void __launch_bounds__(kQueueThreads, MINB)
 k_fast_group(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayout L, int count, int nLights,
              uint32_t stagedBytes, uint32_t numGroups, uint32_t S, float wPrev)
@@ -1095,7 +1079,7 @@ k_fast_group(DrawParams p, const unsigned char* __restrict__ blob, SceneBlobLayo
     if (threadIdx.x == 0) { float wp; blend_weights(p, sW, wp); }
     for (int i = threadIdx.x; i < (kQueueThreads / 32) * kGroupOpen * kGroupPix; i += kQueueThreads) (&sAcc[0][0][0])[i] = make_float4(0, 0, 0, 0);
     if (threadIdx.x < (kQueueThreads / 32) * kGroupOpen) (&sRemain[0][0])[threadIdx.x] = 0;
-    SceneView sc = make_view(smem, blob, L, stagedBytes, count, nLights);
+    SceneView sc = make_view<ALLS>(smem, blob, L, stagedBytes, count, nLights);     // ALLS: whole blob staged -> LDS for every section
     float4* sphK = reinterpret_cast<float4*>(smem + L.offSph);
     if (KFORM) build_sphK(sc, sphK);
     __syncthreads();
@@ -1867,7 +1851,9 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
     {
         const int simd = (sc.count + 3) / 4 * 4;
         const int kform = !sc.kformOk ? 0 : (sc.kformMode == 1 || simd > 1024 ? 1 : 2);
-        auto kern = kform == 2 ? k_fast_group<TPT_QUEUE_MINB, 2> : kform == 1 ? k_fast_group<TPT_QUEUE_MINB, 1> : k_fast_group<TPT_QUEUE_MINB, 0>;
+        const bool alls = sc.stagedBytes == sc.layout.totalBytes;
+        auto kern = alls ? (kform == 2 ? k_fast_group<TPT_QUEUE_MINB, 2, true> : kform == 1 ? k_fast_group<TPT_QUEUE_MINB, 1, true> : k_fast_group<TPT_QUEUE_MINB, 0, true>)
+                         : (kform == 2 ? k_fast_group<TPT_QUEUE_MINB, 2, false> : kform == 1 ? k_fast_group<TPT_QUEUE_MINB, 1, false> : k_fast_group<TPT_QUEUE_MINB, 0, false>);
         const size_t dyn8 = kform == 2 ? ((sc.stagedBytes + 127u) & ~127u) + (size_t)simd * 16 : sc.stagedBytes;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn8);
         if (e != cudaSuccess) return e;
