@@ -10,7 +10,7 @@ from test_oracle import golden_scene
 pytestmark = pytest.mark.gpu
 
 W, H = 640, 360
-VARIANTS = (0, 1, 3, 4, 5, 6, 8)
+VARIANTS = (0, 1, 3, 4, 5, 6, 8, 9)
 
 
 @pytest.fixture(scope="module")

@@ -382,6 +382,9 @@ constexpr int kSlabPix = TPT_SLAB_PIX;     // paths per slab (pixels x one sampl
 #define TPT_QUEUE_THREADS 128
 #define TPT_QUEUE_MINB 6
 #endif
+#ifndef TPT_BIG_THREADS
+#define TPT_BIG_THREADS 768      // one CTA per SM for scenes that fill the shared memory (A/B: 1024 = 32 warps at 64 registers)
+#endif
 #ifndef TPT_P1_GROUP
 #define TPT_P1_GROUP 16
 #endif
@@ -1837,7 +1840,7 @@ cudaError_t launch_fast(const DrawParams& p, const SceneDev& sc, int variant, in
         // 768-thread CTA per SM (24 warps share one copy of the geometry instead of 2 CTAs x 4 warps with a copy each)
         const bool big = stagedAl + ((kform >= 2) ? pairBytes : 0) + 4 * 2048 > 36 * 1024 || sc.stagedBytes != sc.layout.totalBytes;
 #define TPT_LAUNCH_QUEUE(T, M, K) return launch_queue_t<T, M, K>(p, sc, numSMs, stream, bandDone, numBands, bandExpected)
-        if (big) { switch (kform) { case 3: TPT_LAUNCH_QUEUE(768, 1, 3); case 2: TPT_LAUNCH_QUEUE(768, 1, 2); case 1: TPT_LAUNCH_QUEUE(768, 1, 1); default: TPT_LAUNCH_QUEUE(768, 1, 0); } }
+        if (big) { switch (kform) { case 3: TPT_LAUNCH_QUEUE(TPT_BIG_THREADS, 1, 3); case 2: TPT_LAUNCH_QUEUE(TPT_BIG_THREADS, 1, 2); case 1: TPT_LAUNCH_QUEUE(TPT_BIG_THREADS, 1, 1); default: TPT_LAUNCH_QUEUE(TPT_BIG_THREADS, 1, 0); } }
         // long draws (many slabs per warp) run 8 CTAs of 64 registers per SM instead of 6 of 80: measured 26.2 vs 25.3 Gray/s at
         // 3840x2160x16spp, but 21.6 vs 21.9 at 1280x720x4spp, where a warp only gets ~12 slabs and the drain of the last ones
         // weighs more with more warps. Variant 9 forces the 8-CTA instance (A/B runs).
