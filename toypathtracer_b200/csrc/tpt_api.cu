@@ -123,10 +123,12 @@ static int fail_msg(tpt_context* ctx, const char* msg)
 
 namespace tpt {
 // sums the per-frame counters of one draw into the running totals
-__global__ void k_accumulate_rays(const unsigned long long* perFrame, int n, unsigned long long* accum)
+// hostMirror (optional): page-locked host memory the caller of tpt_draw reads after the stream sync — the per-frame counts
+// arrive there by this kernel's own stores, which saves the separate 8-byte D2H copy (one DMA round trip per draw).
+__global__ void k_accumulate_rays(const unsigned long long* perFrame, int n, unsigned long long* accum, unsigned long long* hostMirror)
 {
     unsigned long long s = 0;
-    for (int i = 0; i < n; ++i) s += perFrame[i];
+    for (int i = 0; i < n; ++i) { const unsigned long long v = perFrame[i]; s += v; if (hostMirror) hostMirror[i] = v; }
     accum[0] += s;
     accum[1] = s;
 }
@@ -656,7 +658,15 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
     }
     CK(cudaEventRecord(ctx->evStop, stream), "event record");
     ctx->haveTiming = true;
-    k_accumulate_rays<<<1, 1, 0, stream>>>(ctx->dRayCounters, numFrames, ctx->dAccum);
+    const bool wantCounts = outRayCount || outRaysPerFrame;
+    if (wantCounts && numFrames > ctx->hPinnedCap)
+    {
+        if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
+        ctx->hPinned = nullptr; ctx->hPinnedCap = 0;
+        CK(cudaMallocHost(&ctx->hPinned, (size_t)numFrames * sizeof(unsigned long long)), "cudaMallocHost");
+        ctx->hPinnedCap = numFrames;
+    }
+    k_accumulate_rays<<<1, 1, 0, stream>>>(ctx->dRayCounters, numFrames, ctx->dAccum, wantCounts ? ctx->hPinned : nullptr);
     CK(cudaGetLastError(), "accumulate launch");
     ctx->lastLaunches += 1;
 
@@ -673,15 +683,7 @@ int tpt_draw(tpt_context* ctx, int frameCount, int numFrames, int width, int hei
 
     if (outRayCount || outRaysPerFrame)
     {
-        if (numFrames > ctx->hPinnedCap)
-        {
-            if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
-            ctx->hPinned = nullptr; ctx->hPinnedCap = 0;
-            CK(cudaMallocHost(&ctx->hPinned, (size_t)numFrames * sizeof(unsigned long long)), "cudaMallocHost");
-            ctx->hPinnedCap = numFrames;
-        }
-        CK(cudaMemcpyAsync(ctx->hPinned, ctx->dRayCounters, (size_t)numFrames * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream), "D2H counters");
-        CK(cudaStreamSynchronize(stream), "stream sync");
+        CK(cudaStreamSynchronize(stream), "stream sync");     // the counts were stored into hPinned by k_accumulate_rays
         long long total = 0;
         for (int i = 0; i < numFrames; ++i)
         {
