@@ -315,16 +315,22 @@ def main():
     if world == 1:
         # host backbuffer in, host backbuffer out: what a reference shell does per frame
         host = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory().numpy()
+        # every step carries its host -> device copy: by default tpt_set_scene skips the upload when the bytes are the
+        # resident scene's (a shell calls UpdateTest every frame), which would leave this loop without any H2D
+        ctx.set_option("scene_upload_always", 1)
         for s in range(3):
             ctx.set_scene(sph, mats, cam, em)
             ctx.draw(s, 1, W, H, host, flags=0, mode=mode)
         t0 = time.perf_counter()
         e2e_rays = 0
+        upload = 0
         for s in range(e2e_steps):
-            ctx.set_scene(sph, mats, cam, em)                              # scene H2D (UpdateTest + upload)
+            ctx.set_scene(sph, mats, cam, em)                              # scene H2D (UpdateTest + upload of the packed blob)
+            upload += ctx.last_scene_upload_bytes()
             e2e_rays += ctx.draw(args.warmup + s, 1, W, H, host, flags=0, mode=mode)  # kernel + image D2H + count D2H
         e2e_s = time.perf_counter() - t0
-        h2d = scene_bytes + (W * H * 16 if mode == tpt.MODE_EXACT else 0)  # exact mode uploads prev (bit parity)
+        ctx.set_option("scene_upload_always", 0)
+        h2d = upload // e2e_steps + (W * H * 16 if mode == tpt.MODE_EXACT else 0)  # packed blob; exact mode also uploads prev (bit parity)
         d2h = W * H * 16 + 8
         e2e_api = "tpt_set_scene + tpt_draw(host backbuffer) per step, wall clock"
     else:
@@ -332,8 +338,11 @@ def main():
         # state, not a per-step input), all_gather, and rank 0 reads the assembled image + every rank its ray count back
         host = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory()
         band.zero_()
+        ctx.set_option("scene_upload_always", 1)      # a real scene H2D on every rank, every step (see the 1-GPU leg)
+        upload = [0]
         def e2e_step(s):
             ctx.set_scene(sph, mats, cam, em)
+            upload[0] = ctx.last_scene_upload_bytes()
             r = ctx.draw(s * world, world, W, H, band, flags=tpt.kFlagProgressive, mode=mode, rows=(row0, nrows, rstep, 1), stream=sh)
             img = mg.gather_rows(band, H, rank, world)
             if rank == 0:
@@ -351,7 +360,8 @@ def main():
         e2e_s = time.perf_counter() - t0
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
         e2e_rays = mg.sum_ray_counts(e2e_rays, dev)
-        h2d = scene_bytes * world
+        ctx.set_option("scene_upload_always", 0)
+        h2d = upload[0] * world
         d2h = W * H * 16 + 8 * world
         e2e_api = ("per step and rank: tpt_set_scene + tpt_draw(rows rank::N of N frames, device band) + all_gather; "
                    "rank 0 copies the assembled image to pinned host memory; wall clock, max over ranks")

@@ -91,6 +91,8 @@ int tpt_set_spp(tpt_context* ctx, int spp);
  * scene / camera / size / row-range / spp change invalidates the cache. -1 = adaptive: the first call traces one frame,
  * and every time the caller has walked to the end of the cached window and asks for the frame right after it, the next
  * window doubles (1, 2, 4, 8, 16 frames) — no first-call latency; the Test.h shim sets this, TPT_EXACT_LOOKAHEAD overrides),
+ * "scene_upload_always" (default 0; 1: tpt_set_scene uploads the scene blob even when its bytes equal the resident scene's —
+ * bench.py's end-to-end leg, so that every step carries its host -> device copy),
  * "mitsuba_compare" (default 0; DO_MITSUBA_COMPARE of Config.h:25 as a runtime switch, applied by the NEXT
  * tpt_set_scene: constant sky (0.15, 0.21, 0.3) (Test.cpp:226-227) and zero Metal roughness (Test.cpp:143-145); the
  * switch's third effect, zero aperture (Test.cpp:312-313), is camera data: the Test.h shim's UpdateTest applies it). */
@@ -126,6 +128,9 @@ int tpt_read_ray_count(tpt_context* ctx, void* cudaStream, long long* outRays);
 int tpt_last_kernel_ms(tpt_context* ctx, float* outMs);
 /* Number of kernel launches issued by the most recent tpt_draw. */
 int tpt_last_launch_count(tpt_context* ctx);
+/* Bytes the most recent tpt_set_scene copied host -> device: the packed scene blob, or 0 when its bytes were already
+ * resident (a shell calls UpdateTest every frame; option "scene_upload_always" = 1 copies regardless). */
+long long tpt_last_scene_upload_bytes(tpt_context* ctx);
 
 /* Optional epilogue ("next" row of SURVEY §8f): linear float RGBA -> 8-bit sRGB RGBA with Y flip, the
  * presentation step of the reference shells (Cpp/Windows/PixelShader.hlsl:1-15). dst = width*height*4 bytes. */

@@ -146,3 +146,29 @@ def test_identical_scene_is_not_uploaded_twice_but_changes_are_seen(gpu_ctx):
     gpu_ctx.set_scene(sph, mats, cam, em)
     d = np.zeros((H, W, 4), np.float32); gpu_ctx.draw(0, 1, W, H, d, flags=0, mode=0)
     assert not bits_differ(a, d).any()
+
+
+@pytest.mark.gpu
+def test_scene_upload_accounting(libs):
+    """tpt_set_scene skips the copy when the bytes are resident (a shell calls UpdateTest every frame) and says so;
+    "scene_upload_always" (bench.py's end-to-end leg) copies the packed blob every time without invalidating anything."""
+    ctx = libs.Context(0)
+    sph, mats, cam, em = golden_scene()
+    ctx.set_scene(sph, mats, cam, em)
+    first = ctx.last_scene_upload_bytes()
+    assert first >= 46 * 20 + 46 * 36                  # the packed blob holds at least the caller's arrays
+    ctx.set_scene(sph, mats, cam, em)
+    assert ctx.last_scene_upload_bytes() == 0          # same bytes: nothing copied
+    ctx.set_option("scene_upload_always", 1)
+    img = np.zeros((108, 192, 4), np.float32)
+    ctx.set_option("exact_lookahead", 4)
+    rays = []
+    for f in range(4):
+        ctx.set_scene(sph, mats, cam, em)
+        assert ctx.last_scene_upload_bytes() == first
+        rays.append(ctx.draw(f, 1, 192, 108, img, flags=2, mode=0))
+        assert ctx.last_launch_count() == (3 if f == 0 else 2)     # forced re-uploads of identical bytes keep the frame cache
+    ctx.set_option("scene_upload_always", 0); ctx.set_option("exact_lookahead", 0)
+    ref = np.zeros((108, 192, 4), np.float32)
+    assert rays == [ctx.draw(f, 1, 192, 108, ref, flags=2, mode=0) for f in range(4)] and (ref.view(np.uint32) == img.view(np.uint32)).all()
+    ctx.close()

@@ -70,6 +70,7 @@ def _load_lib():
     L.tpt_read_ray_count.argtypes = [vp, vp, ctypes.POINTER(cll)]; L.tpt_read_ray_count.restype = ci
     L.tpt_last_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]; L.tpt_last_kernel_ms.restype = ci
     L.tpt_last_launch_count.argtypes = [vp]; L.tpt_last_launch_count.restype = ci
+    L.tpt_last_scene_upload_bytes.argtypes = [vp]; L.tpt_last_scene_upload_bytes.restype = ctypes.c_longlong
     L.tpt_tonemap_srgb8.argtypes = [vp, vp, ci, ci, ci, vp, ci, vp]; L.tpt_tonemap_srgb8.restype = ci
     L.tpt_tonemap_rgba8.argtypes = [vp, vp, ci, ci, ci, vp, ci, ci, ci, ci, vp]; L.tpt_tonemap_rgba8.restype = ci
     L.tpt_debug_libm.argtypes = [vp, ci, vp, vp, cll]; L.tpt_debug_libm.restype = ci
@@ -198,6 +199,10 @@ class Context:
 
     def last_launch_count(self) -> int:
         return int(self._L.tpt_last_launch_count(self._h))
+
+    def last_scene_upload_bytes(self) -> int:
+        """Bytes the most recent set_scene copied to the device (0: the scene was already resident)."""
+        return int(self._L.tpt_last_scene_upload_bytes(self._h))
 
     # ---- device memory shared between ranks (CUDA IPC), see include/tpt_b200.h
     def mem_alloc(self, nbytes: int) -> DevicePtr:

@@ -48,6 +48,8 @@ struct tpt_context
                               // write-out) when a host-buffer draw can store straight into page-locked memory
     int fastKForm = 2;        // 0: reference-form sweep, 1: expanded form, 2: expanded form with packed pairs (FFMA2); gated per scene by kformOk
     int fastAlphaZero = 0;
+    int sceneUploadAlways = 0;   // 1: tpt_set_scene copies the blob even when its bytes are the resident scene's (benchmarks: a real H2D per step)
+    long long lastSceneUploadBytes = 0;
     uint32_t sceneFlags = 0;  // kScene* bits for the next tpt_set_scene    // 1: fast-mode draws whose `prev` has zero weight write alpha = 0 instead of preserving it
     int exactLanes = 0;
     // Exact mode, one frame per call (the drop-in's DrawTest): a frame is only `height` serial RNG chains, far too few to
@@ -278,7 +280,8 @@ int tpt_set_scene(tpt_context* ctx, const void* spheres20, const void* materials
     // A reference shell calls UpdateTest + upload every frame although the scene only changes under kFlagAnimate
     // (Test.cpp:304-308): identical bytes are not uploaded again.
     const bool same = ctx->haveScene && ctx->scene.count == count && ctx->scene.layout.flags == L.flags && blob == ctx->lastBlob;
-    if (!same)
+    ctx->lastSceneUploadBytes = 0;
+    if (!same || ctx->sceneUploadAlways)
     {
         const int slot = ctx->haveScene ? (ctx->curBlob ^ 1) : 0;
         // the slot's previous contents may still be read by draws issued before the last upload (device side: the
@@ -303,8 +306,9 @@ int tpt_set_scene(tpt_context* ctx, const void* spheres20, const void* materials
         CK(cudaMemcpyAsync(ctx->dBlobs[slot], ctx->hBlob[slot], blob.size(), cudaMemcpyHostToDevice, ctx->uploadStream), "scene upload");
         CK(cudaEventRecord(ctx->uploadDone[slot], ctx->uploadStream), "upload event");
         ctx->curBlob = slot;
+        ctx->lastSceneUploadBytes = (long long)blob.size();
         ctx->lastBlob.swap(blob);
-        ++ctx->sceneGen;
+        if (!same) ++ctx->sceneGen;              // a forced re-upload of identical bytes is not a new scene (frame-lookahead key)
     }
     ctx->scene.blob = ctx->dBlobs[ctx->curBlob];
     ctx->scene.layout = L;
@@ -355,6 +359,7 @@ int tpt_set_option(tpt_context* ctx, const char* key, int value)
     if (!strcmp(key, "register_host")) { ctx->registerHost = value ? 1 : 0; return 0; }
     if (!strcmp(key, "fast_kform")) { if (value < 0 || value > 2) return fail_msg(ctx, "fast_kform: 0..2"); ctx->fastKForm = value; return 0; }
     if (!strcmp(key, "fast_alpha_zero")) { ctx->fastAlphaZero = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "scene_upload_always")) { ctx->sceneUploadAlways = value ? 1 : 0; return 0; }
     if (!strcmp(key, "mitsuba_compare")) { ctx->sceneFlags = value ? (ctx->sceneFlags | kSceneMitsuba) : (ctx->sceneFlags & ~(uint32_t)kSceneMitsuba); return 0; }
     if (!strcmp(key, "host_progress")) { ctx->hostProgress = value ? 1 : 0; return 0; }
     if (!strcmp(key, "host_zero_copy")) { ctx->hostZeroCopy = value ? 1 : 0; return 0; }
@@ -720,6 +725,7 @@ int tpt_last_kernel_ms(tpt_context* ctx, float* outMs)
 }
 
 int tpt_last_launch_count(tpt_context* ctx) { return ctx ? ctx->lastLaunches : 0; }
+long long tpt_last_scene_upload_bytes(tpt_context* ctx) { return ctx ? ctx->lastSceneUploadBytes : 0; }
 
 int tpt_tonemap_rgba8(tpt_context* ctx, const float* image, int imageOnDevice, int width, int height,
                       unsigned char* dst, int dstOnDevice, int transfer, int bgr, int flipY, void* cudaStreamArg)
