@@ -11,8 +11,9 @@ call of the reference (UpdateTest + DrawTest): ~16.8 M rays (camera + bounce + s
           (CUDA events on the launching stream, one pair per step, summed; L2 flushed between steps, flush not
           timed), max over ranks.
   e2e     the same metric through the drop-in C-ABI with HOST buffers: per step tpt_set_scene (scene H2D, what
-          UpdateTest+GetSceneDesc+UpdateSubresource do in the reference's GPU shells, TestWin.cpp:258-283) +
-          tpt_draw (kernel, image D2H to pinned host memory, ray count D2H), wall clock around the synchronous call.
+          UpdateTest+GetSceneDesc+UpdateSubresource do in the reference's GPU shells, TestWin.cpp:258-283; the
+          option "scene_upload_always" makes it a real copy every step although the bytes do not change) +
+          tpt_draw (kernel, image and ray count into pinned host memory), wall clock around the synchronous call.
   N > 1   north_star's tiled image split, weak scaling: step s renders the N frames s*N .. s*N+N-1 of ONE 1280x720
           image (accumulated with kFlagProgressive); rank r traces rows r, r+N, ... of all N frames (rows are the
           independent RNG chains, Test.cpp:278-280) into its packed band, then ONE all_gather per step assembles the
