@@ -13,6 +13,8 @@ L_k2 = line_of("struct FastHitterK2")
 L_k2_hit = line_of("int hit(const SceneView&", L_k2)
 L_k2_pass2 = line_of("while (cand)", L_k2)
 L_k2c = line_of("struct FastHitterK2C")
+L_k2c_pass2 = line_of("while (cand)", L_k2c)
+L_pairs = line_of("void build_sph_pairs_from_r2(")
 L_step = line_of("bool path_step(")
 L_light = line_of("if (wantLight)", L_step)
 L_queue = line_of("k_fast_queue(DrawParams p")
@@ -27,6 +29,8 @@ def phase(f, ln):
         if L_k2 <= ln < L_k2_hit: return "pass 2 (candidates)"              # the hitter's LDS.128 helper
         if L_k2_hit <= ln < L_k2_pass2: return "sweep setup (ray constants)"
         if L_k2_pass2 <= ln < L_k2c: return "pass 2 (candidates)"
+        if L_k2c <= ln < L_k2c_pass2: return "sweep setup (ray constants)"
+        if L_k2c_pass2 <= ln < L_pairs: return "pass 2 (candidates)"
         if L_step <= ln < L_light: return "shade: hit point, material branches"
         if L_light <= ln < L_queue: return "shade: light sample / continue"
         if L_gen <= ln < L_qpath: return "regeneration: slab ray generation"
